@@ -1,0 +1,187 @@
+"""Golden-case catalogue shared by the fixture generator and the parity tests.
+
+TEST INFRASTRUCTURE.  Each case names a transform spec (class name + kwargs,
+the reference's own spelling), a global torch seed, and how to synthesise the
+inputs.  ``tests/golden/generate.py`` runs the real reference on these and
+stores outputs + sampled params; the tests replay the stored params through
+the oracle (CPU) and the CUDA path (GPU) and compare.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def _affine(spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), tilt=0.0):
+    """Voxel->world 4x4 (float64) with optional small in-plane rotation."""
+    m = np.eye(4, dtype=np.float64)
+    c, s = np.cos(tilt), np.sin(tilt)
+    direction = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    m[:3, :3] = direction * np.asarray(spacing, dtype=np.float64)
+    m[:3, 3] = origin
+    return m
+
+
+def scalar_volume(shape, seed, channels=1, shift=0.0):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.rand((channels, *shape), generator=gen) - shift
+
+
+def label_volume(shape, dtype=torch.int16, channels=1):
+    """Concentric boxes with labels 0..4 (deterministic, no RNG)."""
+    i, j, k = (torch.arange(n, dtype=torch.float32) for n in shape)
+    ci, cj, ck = ((n - 1) / 2 for n in shape)
+    di = (i - ci).abs()[:, None, None] / max(shape[0], 1)
+    dj = (j - cj).abs()[None, :, None] / max(shape[1], 1)
+    dk = (k - ck).abs()[None, None, :] / max(shape[2], 1)
+    d = torch.maximum(torch.maximum(di, dj), dk)  # in [0, 0.5]
+    lab = (4 - torch.clamp((d * 10).floor(), max=4)).to(dtype)
+    return lab[None].repeat(channels, 1, 1, 1).contiguous()
+
+
+def build_inputs(case):
+    shape = tuple(case["shape"])
+    affine = _affine(
+        case.get("spacing", (1.0, 1.0, 1.0)),
+        case.get("origin", (0.0, 0.0, 0.0)),
+        case.get("tilt", 0.0),
+    )
+    subjects = []
+    for b in range(case["batch"]):
+        sub = {}
+        for name, kind in case["images"].items():
+            if kind == "scalar":
+                seed = 1000 + b + 97 * len(sub)
+                tensor = scalar_volume(
+                    shape,
+                    seed,
+                    channels=case.get("channels", 1),
+                    shift=case.get("shift", 0.0),
+                )
+                sub[name] = ("scalar", tensor, affine)
+            else:
+                dtype = getattr(torch, kind)
+                sub[name] = ("label", label_volume(shape, dtype), affine)
+        subjects.append(sub)
+    return {"subjects": subjects}
+
+
+_AFF = {"scales": (0.9, 1.1), "degrees": (-10, 10), "translation": (-3, 3)}
+
+CASES = [
+    # BASELINE.json configs[0]: correctness plumbing case.
+    dict(name="config1_affine_deg10_64", seed=1234, shape=(64, 64, 64), batch=1,
+         images={"t1": "scalar"}, transform=("Affine", {"degrees": 10})),
+    dict(name="affine_b1_label", seed=11, shape=(20, 17, 13), batch=1,
+         images={"t1": "scalar", "seg": "int16"}, transform=("Affine", _AFF)),
+    dict(name="affine_b3_aniso", seed=12, shape=(18, 15, 12), batch=3,
+         spacing=(0.8, 1.1, 2.0), origin=(-7.0, 3.5, 10.0), tilt=0.1,
+         images={"t1": "scalar", "seg": "uint8"}, transform=("Affine", _AFF)),
+    dict(name="affine_fill_zero", seed=13, shape=(16, 14, 12), batch=2,
+         images={"t1": "scalar"},
+         transform=("Affine", {**_AFF, "default_pad_value": 0.0})),
+    dict(name="affine_fill_number", seed=14, shape=(16, 14, 12), batch=2,
+         images={"t1": "scalar", "seg": "int32"},
+         transform=("Affine", {**_AFF, "default_pad_value": -1.5,
+                               "default_pad_label": 7})),
+    dict(name="affine_nearest_image", seed=15, shape=(16, 14, 12), batch=2,
+         images={"t1": "scalar"},
+         transform=("Affine", {**_AFF, "image_interpolation": "nearest"})),
+    dict(name="affine_gated", seed=16, shape=(12, 12, 10), batch=5,
+         images={"t1": "scalar", "seg": "int64"},
+         transform=("Affine", {**_AFF, "p": 0.5})),
+    dict(name="affine_multichannel", seed=17, shape=(12, 11, 10), batch=2,
+         channels=3, shift=0.4, images={"t1": "scalar"},
+         transform=("Affine", _AFF)),
+    dict(name="elastic_b1", seed=21, shape=(24, 20, 16), batch=1,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("ElasticDeformation", {"max_displacement": 2.0})),
+    dict(name="elastic_b3_aniso", seed=22, shape=(20, 18, 14), batch=3,
+         spacing=(0.8, 1.1, 2.0), origin=(2.0, -3.0, 1.0),
+         images={"t1": "scalar", "seg": "int32"},
+         transform=("ElasticDeformation",
+                    {"max_displacement": (1.0, 3.0),
+                     "num_control_points": (5, 6, 7), "locked_borders": 1})),
+    dict(name="spatial_affine_first", seed=23, shape=(18, 16, 14), batch=2,
+         spacing=(1.2, 0.9, 1.5),
+         images={"t1": "scalar", "seg": "uint8"},
+         transform=("Spatial", {**_AFF, "max_displacement": (1.0, 2.5),
+                                "num_control_points": 6})),
+    dict(name="spatial_elastic_first", seed=24, shape=(18, 16, 14), batch=2,
+         spacing=(1.2, 0.9, 1.5),
+         images={"t1": "scalar", "seg": "uint8"},
+         transform=("Spatial", {**_AFF, "max_displacement": (1.0, 2.5),
+                                "num_control_points": 6,
+                                "affine_first": False})),
+    dict(name="spatial_shared", seed=25, shape=(14, 13, 12), batch=3,
+         images={"t1": "scalar"},
+         transform=("Spatial", {**_AFF, "max_displacement": 1.5,
+                                "per_instance": False})),
+    dict(name="bias_b1", seed=31, shape=(20, 17, 13), batch=1,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("BiasField", {})),
+    dict(name="bias_b3_gated", seed=32, shape=(16, 14, 12), batch=4,
+         channels=2, images={"t1": "scalar"},
+         transform=("BiasField", {"std": (0.1, 0.6), "p": 0.6})),
+    dict(name="bias_shared", seed=33, shape=(16, 14, 12), batch=3,
+         images={"t1": "scalar"},
+         transform=("BiasField", {"per_instance": False})),
+    dict(name="bias_large_scale", seed=34, shape=(40, 30, 20), batch=2,
+         images={"t1": "scalar"},
+         transform=("BiasField", {"scale": 0.3})),
+    dict(name="blur_b1", seed=41, shape=(20, 17, 13), batch=1,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Blur", {"std": (0.5, 2.0)})),
+    dict(name="blur_b3_aniso", seed=42, shape=(18, 15, 12), batch=3,
+         spacing=(0.8, 1.1, 2.0), images={"t1": "scalar"},
+         transform=("Blur", {"std": (0.0, 2.0)})),
+    dict(name="blur_shared", seed=43, shape=(16, 14, 12), batch=3, channels=2,
+         images={"t1": "scalar"},
+         transform=("Blur", {"std": (0.5, 2.0), "per_instance": False})),
+    dict(name="blur_gated", seed=44, shape=(12, 12, 10), batch=5,
+         images={"t1": "scalar"},
+         transform=("Blur", {"std": (0.5, 2.0), "p": 0.5})),
+    dict(name="blur_one_axis", seed=45, shape=(12, 12, 10), batch=1,
+         images={"t1": "scalar"},
+         transform=("Blur", {"std": (0.0, 1.3, 0.0)})),
+    dict(name="noise_b1", seed=51, shape=(20, 17, 13), batch=1,
+         images={"t1": "scalar", "seg": "int16"}, transform=("Noise", {})),
+    dict(name="noise_b3_two_images", seed=52, shape=(16, 16, 16), batch=3,
+         images={"t1": "scalar", "t2": "scalar"},
+         transform=("Noise", {"mean": (-0.1, 0.1), "std": (0.0, 0.25)})),
+    dict(name="noise_ragged_tail", seed=53, shape=(5, 7, 3), batch=2,
+         images={"t1": "scalar", "t2": "scalar"},
+         transform=("Noise", {"std": (0.0, 0.25)})),
+    dict(name="noise_rician_gated", seed=54, shape=(12, 12, 10), batch=5,
+         shift=0.3, images={"t1": "scalar"},
+         transform=("Noise", {"std": (0.05, 0.25), "rician": True, "p": 0.5})),
+    dict(name="gamma_b1", seed=61, shape=(20, 17, 13), batch=1, shift=0.3,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Gamma", {"log_gamma": (-0.3, 0.3)})),
+    dict(name="gamma_b4_gated", seed=62, shape=(12, 12, 10), batch=4,
+         shift=0.3, images={"t1": "scalar"},
+         transform=("Gamma", {"log_gamma": (-0.3, 0.3), "p": 0.7})),
+    dict(name="compose_config2_b2", seed=71, shape=(24, 20, 16), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=[("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)}),
+                    ("ElasticDeformation", {"max_displacement": 2.0})]),
+    dict(name="compose_full_b2", seed=72, shape=(24, 20, 16), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=[("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)}),
+                    ("ElasticDeformation", {"max_displacement": 2.0}),
+                    ("BiasField", {}),
+                    ("Blur", {"std": (0.0, 2.0)}),
+                    ("Noise", {"std": (0.0, 0.25)}),
+                    ("Gamma", {"log_gamma": (-0.3, 0.3)})]),
+    dict(name="compose_full_b1_48", seed=73, shape=(48, 48, 48), batch=1,
+         images={"t1": "scalar"},
+         transform=[("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)}),
+                    ("ElasticDeformation", {}),
+                    ("BiasField", {}),
+                    ("Blur", {"std": (0.0, 2.0)}),
+                    ("Noise", {"std": (0.0, 0.25)}),
+                    ("Gamma", {"log_gamma": (-0.3, 0.3)})]),
+]
+
+CASES_BY_NAME = {c["name"]: c for c in CASES}
