@@ -1,0 +1,191 @@
+/*
+ * tio_b200.h — C-ABI of the B200-native 3-D augmentation hot path.
+ *
+ * Drop-in boundary for the TorchIO v2 (2.0.0a2 @ 2b019d2) transform kernels.
+ * The reference has no FFI layer: its seam is the Python method
+ *   Transform.apply_transform(batch, params)        transforms/transform.py:408-427
+ * and, one level down, the plain-tensor helpers each entry point below
+ * replaces (cited per function; paths relative to src/torchio/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Volumes are contiguous (B, C, I, J, K), K fastest, in DEVICE memory.
+ *   - Parameter tables are DEVICE pointers unless marked "host"; callers pack
+ *     them into one pinned staging buffer and upload it once per launch.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - Every function returns 0 on success, non-zero on error;
+ *     tio_last_error() returns a thread-local message.  No exceptions cross
+ *     the boundary, no global mutable state, re-entrant from several threads
+ *     (the reference calls transforms from Queue's ThreadPoolExecutor,
+ *     data/queue.py:119-123).
+ *   - Outputs are caller-allocated; the library keeps no pointer after return.
+ */
+#ifndef TIO_B200_H
+#define TIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIO_ABI_VERSION 1
+
+/* element types accepted by tio_resample (images: F32; label maps: the rest) */
+enum tio_dtype {
+  TIO_F32 = 0,
+  TIO_U8 = 1,
+  TIO_I8 = 2,
+  TIO_I16 = 3,
+  TIO_I32 = 4,
+  TIO_I64 = 5
+};
+
+enum tio_interp { TIO_NEAREST = 0, TIO_LINEAR = 1 };
+
+/* per-element flag bits for tio_resample */
+#define TIO_FLAG_PASSTHROUGH 1u /* copy the row bit-exactly (spatial.py:1101-1106) */
+#define TIO_FLAG_ELASTIC 2u     /* the element has a control-point grid */
+
+const char* tio_last_error(void);
+int tio_abi_version(void);
+
+/*
+ * K1 — fused resample: affine matrix + trilinear control-point displacement +
+ * 8-tap / nearest gather + out-of-bounds fill + pass-through rows, one pass.
+ *
+ * Replaces _build_sampling_grid + _sample_batch[_per_sample]
+ *   (transforms/spatial/spatial.py:1504-1579, 1651-1731, 1764-1857)
+ * i.e. arange/meshgrid/cat/matmul, F.interpolate(trilinear, align_corners),
+ * two F.grid_sample(zeros, align_corners=True) passes and torch.where.
+ *
+ *   src, dst   (B, C, I, J, K) / (B, C, OI, OJ, OK) of `dtype`
+ *   mat        [B][12] fp32: rows 0..2 of inv(A_in) @ inv(T) @ A_out
+ *              (float64 product cast to fp32, spatial.py:1594-1601)
+ *   cp         [B][ni][nj][nk][3] fp32 displacements in mm, or NULL
+ *   flags      [B] bytes (TIO_FLAG_*), or NULL (= 0 for every element)
+ *   spacing_in/out  host float[3]: fp32 casts of the affine column norms
+ *              (spatial.py:1559-1568)
+ *   affine_first    spatial.py:1570-1577
+ *   mode       TIO_NEAREST | TIO_LINEAR (spatial.py:150-153)
+ *   fill       [C] fp32 per-channel fill, or NULL = skip the mask step
+ *              (the reference skips it only for a python-float 0.0 fill,
+ *              spatial.py:2072-2076).  The mask is always the TRILINEAR
+ *              in-bounds weight sum, even for nearest data (:1722-1727).
+ * src and dst must not alias.
+ */
+int tio_resample(const void* src, void* dst, int dtype,
+                 int B, int C, int I, int J, int K,
+                 int OI, int OJ, int OK,
+                 const float* mat, const float* cp, const uint8_t* flags,
+                 int ni, int nj, int nk,
+                 const float* spacing_in, const float* spacing_out,
+                 int affine_first, int mode, const float* fill,
+                 void* stream);
+
+/*
+ * Per-channel minimum of batch element 0 -> fill[C] on the device, no host
+ * sync.  Replaces _batch_fill_value("minimum") = tensor.min().item()
+ * (spatial.py:2054-2060, 2094-2095).  `src` is (B, C, n) fp32, n = I*J*K.
+ */
+int tio_min_sample0(const float* src, int C, int64_t n, float* fill, void* stream);
+
+/*
+ * K2 — bias field: dst = src * exp(trilerp_align_corners(coarse)) (or / for
+ * the inverse).  Replaces _apply_bias_per_element / _generate_bias_field
+ * (transforms/intensity/bias_field.py:201-255, 296-341).
+ *   coarse    [B][C][si][sj][sk] fp32, drawn on the host by torch.normal from
+ *             the recorded seeds (bias_field.py:281-293,316-329)
+ *   identity  [B] bytes, non-zero = copy the row exactly (std == 0), or NULL
+ * In-place (src == dst) allowed.
+ */
+int tio_bias_field(const float* src, float* dst, int B, int C, int I, int J, int K,
+                   const float* coarse, int si, int sj, int sk,
+                   const uint8_t* identity, int divide, void* stream);
+
+/*
+ * K3 — separable Gaussian blur with replicate (clamp) addressing, axes I, J,
+ * K in that order.  Replaces _gaussian_smooth{,_shared,_per_element}
+ * (transforms/intensity/blur.py:129-252) = 3 x (F.pad replicate + F.conv3d).
+ *   taps      [3][B][2R+1] fp32, centred, normalised on the host exactly as
+ *             blur.py:179-183 / 292-328 (zero beyond each element's radius,
+ *             delta kernel where sigma <= 0)
+ *   radius    [3][B] int32: the element's own radius on that axis (0 = skip)
+ *   R         table half-width (max radius over the whole table)
+ *   identity  [B] bytes: rows with all sigma <= 0 are copied exactly
+ *   scratch   device buffer of B*C*I*J*K floats (may be NULL if at most one
+ *             axis is active for every element)
+ * src and dst must not alias.
+ */
+int tio_blur(const float* src, float* dst, float* scratch,
+             int B, int C, int I, int J, int K,
+             const float* taps, const int32_t* radius, int R,
+             const uint8_t* identity, void* stream);
+
+/*
+ * K4a — exact replay of torch's CPU `randn` stream on the device:
+ * mt19937(seed) -> 24-bit uniforms -> 16-wide Box-Muller blocks, element
+ * `offset`..`offset+n` of the flat stream (ATen normal_fill; the layout the
+ * reference depends on through torch.randn(generator=CPU), noise.py:177).
+ * Requires offset % 16 == 0 and n % 16 == 0 (ragged tails stay on the host).
+ */
+int tio_randn_mt19937(uint64_t seed, uint64_t offset, uint64_t n, float* z, void* stream);
+
+/*
+ * K4 — additive Gaussian / Rician noise.  Replaces _sample_noise + add +
+ * _restore_gated_out (transforms/intensity/noise.py:98-178).
+ *   dst = src + (mean[b] + std[b] * z)                       (Gaussian)
+ *   dst = sqrt((src + n1)^2 + n2^2), n_i = mean + std * z_i  (Rician)
+ *   z, z2    standard normals, same shape as src (z2 NULL unless Rician)
+ *   keep     [B] bytes or NULL; rows with keep == 0 are copied exactly
+ * In-place allowed.
+ */
+int tio_noise(const float* src, float* dst, int B, int64_t per_elem,
+              const float* mean, const float* std, const uint8_t* keep,
+              const float* z, const float* z2, void* stream);
+
+/*
+ * K4b — same, with normals generated in registers from Philox4x32-10 keyed by
+ * (seed, global element index): statistically equivalent, NOT the reference
+ * stream.  `rician` selects the two-draw variant.
+ */
+int tio_noise_philox(const float* src, float* dst, int B, int64_t per_elem,
+                     const float* mean, const float* std, const uint8_t* keep,
+                     uint64_t seed, int rician, void* stream);
+
+/*
+ * K5 — gamma: dst = sign(src) * |src| ^ gamma[b].  Replaces
+ * data.sign() * data.abs().pow(gamma)  (transforms/intensity/gamma.py:88-90).
+ * In-place allowed.
+ */
+int tio_gamma(const float* src, float* dst, int B, int64_t per_elem,
+              const float* gamma, void* stream);
+
+/*
+ * Fused intensity chain (Compose-level fusion of consecutive intensity
+ * transforms; results equal to running K2, K3, K4, K5 one after another up to
+ * fp32 summation order):
+ *   v   = src * exp(bias)            if coarse != NULL
+ *   v   = blur_K(blur_J(blur_I(v)))  if taps   != NULL
+ *   v   = v + mean + std * z         if z      != NULL
+ *   dst = sign(v) |v|^gamma          if gamma  != NULL
+ * Per-element identity flags as in the individual kernels
+ * (bias_identity / blur_identity / keep).  src and dst must not alias when
+ * taps != NULL.
+ */
+int tio_intensity_fused(const float* src, float* dst, float* scratch,
+                        int B, int C, int I, int J, int K,
+                        const float* coarse, int si, int sj, int sk,
+                        const uint8_t* bias_identity,
+                        const float* taps, const int32_t* radius, int R,
+                        const uint8_t* blur_identity,
+                        const float* mean, const float* std, const uint8_t* keep,
+                        const float* z,
+                        const float* gamma,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIO_B200_H */
