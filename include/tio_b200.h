@@ -113,6 +113,8 @@ int tio_bias_field(const float* src, float* dst, int B, int C, int I, int J, int
  *             delta kernel where sigma <= 0)
  *   radius    [3][B] int32: the element's own radius on that axis (0 = skip)
  *   R         table half-width (max radius over the whole table)
+ *   axes_mask host int, bit a set = axis a is active for at least one element
+ *             (lets the library skip whole passes without reading `radius`)
  *   identity  [B] bytes: rows with all sigma <= 0 are copied exactly
  *   scratch   device buffer of B*C*I*J*K floats (may be NULL if at most one
  *             axis is active for every element)
@@ -120,24 +122,16 @@ int tio_bias_field(const float* src, float* dst, int B, int C, int I, int J, int
  */
 int tio_blur(const float* src, float* dst, float* scratch,
              int B, int C, int I, int J, int K,
-             const float* taps, const int32_t* radius, int R,
+             const float* taps, const int32_t* radius, int R, int axes_mask,
              const uint8_t* identity, void* stream);
-
-/*
- * K4a — exact replay of torch's CPU `randn` stream on the device:
- * mt19937(seed) -> 24-bit uniforms -> 16-wide Box-Muller blocks, element
- * `offset`..`offset+n` of the flat stream (ATen normal_fill; the layout the
- * reference depends on through torch.randn(generator=CPU), noise.py:177).
- * Requires offset % 16 == 0 and n % 16 == 0 (ragged tails stay on the host).
- */
-int tio_randn_mt19937(uint64_t seed, uint64_t offset, uint64_t n, float* z, void* stream);
 
 /*
  * K4 — additive Gaussian / Rician noise.  Replaces _sample_noise + add +
  * _restore_gated_out (transforms/intensity/noise.py:98-178).
  *   dst = src + (mean[b] + std[b] * z)                       (Gaussian)
  *   dst = sqrt((src + n1)^2 + n2^2), n_i = mean + std * z_i  (Rician)
- *   z, z2    standard normals, same shape as src (z2 NULL unless Rician)
+ *   z, z2    standard normals, same shape as src (z2 NULL unless Rician); the
+ *            reference draws them with torch.randn on a CPU mt19937 generator
  *   keep     [B] bytes or NULL; rows with keep == 0 are copied exactly
  * In-place allowed.
  */
@@ -161,29 +155,6 @@ int tio_noise_philox(const float* src, float* dst, int B, int64_t per_elem,
  */
 int tio_gamma(const float* src, float* dst, int B, int64_t per_elem,
               const float* gamma, void* stream);
-
-/*
- * Fused intensity chain (Compose-level fusion of consecutive intensity
- * transforms; results equal to running K2, K3, K4, K5 one after another up to
- * fp32 summation order):
- *   v   = src * exp(bias)            if coarse != NULL
- *   v   = blur_K(blur_J(blur_I(v)))  if taps   != NULL
- *   v   = v + mean + std * z         if z      != NULL
- *   dst = sign(v) |v|^gamma          if gamma  != NULL
- * Per-element identity flags as in the individual kernels
- * (bias_identity / blur_identity / keep).  src and dst must not alias when
- * taps != NULL.
- */
-int tio_intensity_fused(const float* src, float* dst, float* scratch,
-                        int B, int C, int I, int J, int K,
-                        const float* coarse, int si, int sj, int sk,
-                        const uint8_t* bias_identity,
-                        const float* taps, const int32_t* radius, int R,
-                        const uint8_t* blur_identity,
-                        const float* mean, const float* std, const uint8_t* keep,
-                        const float* z,
-                        const float* gamma,
-                        void* stream);
 
 #ifdef __cplusplus
 }

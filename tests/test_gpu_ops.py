@@ -1,0 +1,191 @@
+"""GPU parity at the ops / C-ABI level against the C oracle on seeded random
+parameters, including the edge cases the reference's tests exercise: 2-D
+inputs, odd shapes, large rotations, coordinates far out of bounds,
+pass-through rows, multi-channel data, every label dtype."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _orc():
+    from oracle import c_port
+
+    return c_port
+
+
+def _random_matrix(rng, shape, big=False):
+    ang = rng.uniform(-0.6, 0.6, 3) if big else rng.uniform(-0.2, 0.2, 3)
+    cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    rs = rz @ ry @ rx @ np.diag(rng.uniform(0.8, 1.25, 3))
+    c = (np.asarray(shape) - 1) / 2
+    m = np.eye(4)
+    m[:3, :3] = rs
+    m[:3, 3] = c - rs @ c + rng.uniform(-4, 4, 3) * (5 if big else 1)
+    return m.astype(np.float32)[:3].reshape(12)
+
+
+def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill):
+    from torchio_b200 import ops
+
+    c_port = _orc()
+    b, c = data.shape[:2]
+    shape = data.shape[2:]
+    dev = torch.device("cuda")
+    mat_t = torch.as_tensor(mat)
+    cp_t = None if cp is None else torch.as_tensor(cp)
+    fl_t = None if flags is None else torch.as_tensor(flags)
+    fill_t = None if fill is None else torch.as_tensor(fill, dtype=torch.float32)
+    got = ops.resample(
+        data.to(dev), mat_t.to(dev), None if cp_t is None else cp_t.to(dev),
+        None if fl_t is None else fl_t.to(dev), sp_in, sp_out, affine_first=affine_first,
+        mode=mode, fill=None if fill_t is None else fill_t.to(dev),
+    ).cpu()
+    want = torch.empty_like(data)
+    ni, nj, nk = (0, 0, 0) if cp is None else cp.shape[1:4]
+    spi = torch.as_tensor(np.asarray(sp_in, dtype=np.float32))
+    spo = torch.as_tensor(np.asarray(sp_out, dtype=np.float32))
+    p = c_port._p
+    rc = c_port.lib().orc_resample(
+        p(data), p(want), c_port._DTYPES[data.dtype], b, c, *shape, *shape, p(mat_t), p(cp_t),
+        p(fl_t), ni, nj, nk, p(spi), p(spo), int(affine_first), mode, p(fill_t),
+    )
+    assert rc == 0
+    return got, want
+
+
+SHAPES = [(33, 29, 70), (16, 16, 1), (7, 5, 3), (64, 48, 40)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("elastic", [False, True])
+def test_resample_bit_exact_vs_c_oracle(shape, mode, elastic):
+    rng = np.random.default_rng(hash((shape, mode, elastic)) % 2**32)
+    b, c = 3, 2
+    g = torch.Generator().manual_seed(5)
+    data = torch.rand((b, c, *shape), generator=g) - 0.25
+    mat = np.stack([_random_matrix(rng, shape, big=(i == 1)) for i in range(b)])
+    flags = np.zeros(b, dtype=np.uint8)
+    cp = None
+    if elastic:
+        cp = rng.uniform(-3, 3, (b, 5, 6, 7, 3)).astype(np.float32)
+        flags[:] = 2
+        flags[2] = 0  # one element without a grid
+    for affine_first in ((True, False) if elastic else (True,)):
+        for fill in (None, np.array([-1.0, 0.5], dtype=np.float32)):
+            got, want = _run_both(data, mat, cp, flags, (0.8, 1.1, 2.0), (0.8, 1.1, 2.0),
+                                  affine_first, mode, fill)
+            assert torch.equal(got, want), int((got != want).sum())
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64])
+def test_label_dtypes_nearest_exact(dtype):
+    rng = np.random.default_rng(3)
+    shape = (20, 18, 37)
+    lo, hi = (0, 200) if dtype == torch.uint8 else (-100, 100)
+    data = torch.randint(lo, hi, (2, 1, *shape), dtype=torch.int64).to(dtype)
+    mat = np.stack([_random_matrix(rng, shape) for _ in range(2)])
+    for fill in (None, np.array([7.0], dtype=np.float32)):
+        got, want = _run_both(data, mat, None, None, (1, 1, 1), (1, 1, 1), True, 0, fill)
+        assert torch.equal(got, want)
+
+
+def test_passthrough_rows_are_bit_copies_and_far_oob_is_fill():
+    rng = np.random.default_rng(9)
+    shape = (12, 10, 33)
+    data = torch.rand((3, 1, *shape))
+    mat = np.stack([_random_matrix(rng, shape) for _ in range(3)])
+    mat[2, 3] = 1e6  # everything out of bounds
+    flags = np.array([1, 0, 0], dtype=np.uint8)
+    fill = np.array([0.25], dtype=np.float32)
+    got, want = _run_both(data, mat, None, flags, (1, 1, 1), (1, 1, 1), True, 1, fill)
+    assert torch.equal(got, want)
+    assert torch.equal(got[0], data[0])
+    assert bool((got[2] == 0.25).all())
+
+
+def test_min_sample0():
+    from torchio_b200 import ops
+
+    for shape in ((2, 3, 16, 16, 16), (1, 2, 5, 7, 3)):
+        x = torch.rand(shape) - 0.7
+        got = ops.min_sample0(x.cuda()).cpu()
+        assert torch.equal(got, x[0].reshape(shape[1], -1).min(dim=1).values)
+
+
+def test_intensity_kernels_vs_c_oracle():
+    from torchio_b200 import ops
+
+    c_port = _orc()
+    p = c_port._p
+    lib = c_port.lib()
+    g = torch.Generator().manual_seed(11)
+    for shape in ((3, 2, 24, 20, 16), (2, 1, 9, 7, 5)):
+        b, c = shape[:2]
+        x = torch.rand(shape, generator=g) - 0.3
+        n = x[0].numel()
+        # bias
+        coarse = torch.randn((b, c, 4, 5, 6), generator=g) * 0.5
+        ident = torch.tensor([0, 1, 0][:b], dtype=torch.uint8)
+        for divide in (0, 1):
+            want = torch.empty_like(x)
+            lib.orc_bias_field(p(x), p(want), b, c, *shape[2:], p(coarse), 4, 5, 6, p(ident), divide)
+            got = ops.bias_field(x.cuda(), coarse.cuda(), ident.cuda(), divide=bool(divide)).cpu()
+            assert (got - want).abs().max() <= 2e-6 * float(want.abs().max())
+            assert torch.equal(got[1], x[1])
+        # blur
+        from torchio_b200 import tables
+
+        sig = np.array([[0.7, 0.0, 1.9], [0.0, 0.0, 0.0], [1.2, 0.6, 0.4]][:b])
+        t = tables.blur_tables(sig, b)
+        want = torch.empty_like(x)
+        lib.orc_blur(p(x), p(want), None, b, c, *shape[2:], p(t.taps), p(t.radius), t.big_r,
+                     p(t.identity))
+        got = ops.blur(x.cuda(), t.taps.cuda(), t.radius.cuda(), t.big_r, t.axes_mask,
+                       t.identity.cuda()).cpu()
+        assert (got - want).abs().max() <= 2e-6
+        assert torch.equal(got[1], x[1])
+        # noise (gaussian + rician + keep)
+        z, z2 = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+        mean = torch.tensor([0.1, -0.2, 0.0][:b]); std = torch.tensor([0.2, 0.1, 0.3][:b])
+        keep = torch.tensor([1, 0, 1][:b], dtype=torch.uint8)
+        for zz in (None, z2):
+            want = torch.empty_like(x)
+            lib.orc_noise(p(x), p(want), b, ctypes.c_int64(n), p(mean), p(std), p(keep), p(z), p(zz))
+            got = ops.noise(x.cuda(), mean.cuda(), std.cuda(), keep.cuda(), z.cuda(),
+                            None if zz is None else zz.cuda()).cpu()
+            assert (got - want).abs().max() <= 1e-6
+            assert torch.equal(got[1], x[1])
+        # gamma
+        gam = torch.tensor([0.8, 1.0, 1.3][:b])
+        want = torch.empty_like(x)
+        lib.orc_gamma(p(x), p(want), b, ctypes.c_int64(n), p(gam))
+        got = ops.gamma(x.cuda(), gam.cuda()).cpu()
+        assert (got - want).abs().max() <= 2e-6
+        assert torch.equal(got[1], x[1])
+
+
+def test_philox_noise_statistics():
+    from torchio_b200 import ops
+
+    x = torch.zeros((2, 1, 64, 64, 64), device="cuda")
+    mean = torch.tensor([0.5, -1.0], device="cuda")
+    std = torch.tensor([2.0, 0.5], device="cuda")
+    y = ops.noise_philox(x, mean, std, None, seed=1234).cpu()
+    for b in range(2):
+        assert abs(float(y[b].mean()) - float(mean[b])) < 0.02 * float(std[b]) + 1e-3
+        assert abs(float(y[b].std()) - float(std[b])) < 0.01 * float(std[b])
+    y2 = ops.noise_philox(x, mean, std, None, seed=1234).cpu()
+    assert torch.equal(y, y2)
+    y3 = ops.noise_philox(x, mean, std, None, seed=1235).cpu()
+    assert not torch.equal(y, y3)
+    kurt = float(((y[0] - y[0].mean()) ** 4).mean() / y[0].var() ** 2)
+    assert abs(kurt - 3.0) < 0.05

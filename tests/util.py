@@ -44,3 +44,52 @@ def report(actual: torch.Tensor, expected: torch.Tensor) -> dict:
         "n_mismatch": int((a != e).sum()),
         "n": a.numel(),
     }
+
+
+# ---- product-side helpers -----------------------------------------------------
+
+
+def product_batch(images, device=None):
+    """Oracle-format images dict -> torchio_b200.SubjectsBatch."""
+    import torchio_b200 as tio
+
+    batches = {}
+    for name, img in images.items():
+        cls = tio.LabelMap if img["kind"] == "label" else tio.ScalarImage
+        data = img["data"].clone()
+        if device is not None:
+            data = data.to(device)
+        affines = [tio.AffineMatrix(a) for a in img["affines"]]
+        batches[name] = tio.ImagesBatch(data, affines, image_class=cls)
+    return tio.SubjectsBatch(batches)
+
+
+def make_product_transform(spec):
+    import warnings
+
+    import torchio_b200 as tio
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if isinstance(spec, list):
+            return tio.Compose([make_product_transform(s) for s in spec], copy=False)
+        name, kwargs = spec
+        return getattr(tio, name)(**kwargs)
+
+
+def blank_transform(name):
+    """A transform instance whose apply_transform can replay recorded params."""
+    import warnings
+
+    import torchio_b200 as tio
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return getattr(tio, name)()
+
+
+def product_replay(batch, history):
+    """Apply recorded params through the product's apply_transform (CUDA)."""
+    for step in history:
+        batch = blank_transform(step["name"]).apply_transform(batch, step["params"])
+    return batch

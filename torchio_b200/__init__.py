@@ -1,0 +1,26 @@
+"""torchio_b200 — B200-native 3-D augmentation hot path behind the TorchIO v2 API.
+
+Drop-in for the reference's spatial + intensity augmentation chain
+(`Affine`, `ElasticDeformation`, `Spatial`, `BiasField`, `Blur`, `Noise`,
+`Gamma`, `Compose`) on tensor-backed `Subject` / `SubjectsBatch` data.  The
+tensor math runs in hand-written sm_100a CUDA kernels exposed through the C-ABI
+of ``include/tio_b200.h``; see DESIGN.md and INTEGRATION.md.
+"""
+
+from .data import (AffineMatrix, Image, ImagesBatch, LabelMap, ScalarImage, StudiesBatch,
+                   Subject, SubjectsBatch)
+from .params import Choice
+from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, ElasticDeformation,
+                         Gamma, IntensityTransform, Noise, Spatial, SpatialTransform, Transform,
+                         apply_inverse_transform, execution_device, get_inverse_transform,
+                         set_execution_device)
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose",
+    "ElasticDeformation", "Gamma", "Image", "ImagesBatch", "IntensityTransform", "LabelMap",
+    "Noise", "ScalarImage", "Spatial", "SpatialTransform", "StudiesBatch", "Subject",
+    "SubjectsBatch", "Transform", "apply_inverse_transform", "execution_device",
+    "get_inverse_transform", "set_execution_device",
+]

@@ -1,0 +1,219 @@
+"""Functional, tensor-level API over the C-ABI kernels.
+
+Each function is the plain-tensor replacement of one reference helper
+(cited per function; TorchIO 2.0.0a2, paths relative to
+src/torchio/transforms/).  Inputs are CUDA tensors; parameter tables are
+uploaded with one pinned staging copy per call (`upload`).  Launches go to the
+caller's current CUDA stream on the tensor's device.  No CPU fallback.
+"""
+
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _native
+
+DTYPE_CODES = {
+    torch.float32: 0, torch.uint8: 1, torch.int8: 2,
+    torch.int16: 3, torch.int32: 4, torch.int64: 5,
+}
+NEAREST, LINEAR = 0, 1
+FLAG_PASSTHROUGH, FLAG_ELASTIC = 1, 2
+
+_counter = threading.local()
+
+
+def launches() -> int:
+    """Number of kernels this thread has launched through the library."""
+    return getattr(_counter, "n", 0)
+
+
+def _count(n: int) -> None:
+    _counter.n = getattr(_counter, "n", 0) + n
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"torchio_b200.ops.{name}: expected a CUDA tensor (got {t.device});"
+            " the kernels have no CPU fallback"
+        )
+    if t.requires_grad:
+        raise NotImplementedError(
+            f"torchio_b200.ops.{name}: kernels are forward-only; detach() the input"
+        )
+
+
+def upload(device: torch.device, *arrays):
+    """Pack host arrays into one pinned buffer, copy once, return device views.
+
+    Each array is a numpy array or CPU tensor (or None -> None).  16-byte
+    aligned segments so float4/TMA consumers can read them directly.
+    """
+    specs, offset = [], 0
+    for a in arrays:
+        if a is None:
+            specs.append(None)
+            continue
+        t = torch.as_tensor(a)
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        specs.append((t, offset, nbytes))
+        offset += (nbytes + 15) // 16 * 16
+    if offset == 0:
+        return [None] * len(arrays)
+    stage = torch.empty(offset, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    for s in specs:
+        if s is None:
+            continue
+        t, off, nbytes = s
+        stage[off:off + nbytes] = t.reshape(-1).view(torch.uint8)
+    dev = stage.to(device, non_blocking=True)
+    out = []
+    for s in specs:
+        if s is None:
+            out.append(None)
+            continue
+        t, off, nbytes = s
+        out.append(dev[off:off + nbytes].view(t.dtype).reshape(t.shape))
+    return out
+
+
+def resample(
+    src: Tensor, mat: Tensor, cp: Tensor | None, flags: Tensor | None,
+    spacing_in, spacing_out, *, affine_first: bool, mode: int,
+    fill: Tensor | None, out_shape=None,
+) -> Tensor:
+    """K1.  Replaces _build_sampling_grid + _sample_batch[_per_sample]
+    (spatial/spatial.py:1504-1579,1651-1857).
+
+    src (B,C,I,J,K) fp32 or integer label dtype; mat (B,12) fp32 cuda;
+    cp (B,ni,nj,nk,3) fp32 cuda or None; flags (B,) uint8 cuda or None;
+    fill (C,) fp32 cuda or None (= no mask step).
+    """
+    _require_cuda(src, "resample")
+    if src.dtype not in DTYPE_CODES:
+        raise TypeError(f"resample: unsupported dtype {src.dtype}")
+    src = src.contiguous()
+    b, c, i, j, k = src.shape
+    oi, oj, ok = (i, j, k) if out_shape is None else out_shape
+    dst = torch.empty((b, c, oi, oj, ok), dtype=src.dtype, device=src.device)
+    ni = nj = nk = 0
+    if cp is not None:
+        ni, nj, nk = cp.shape[1:4]
+    sp_in = np.asarray(spacing_in, dtype=np.float32)
+    sp_out = np.asarray(spacing_out, dtype=np.float32)
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_resample", _ptr(src), _ptr(dst), DTYPE_CODES[src.dtype],
+            b, c, i, j, k, oi, oj, ok, _ptr(mat), _ptr(cp), _ptr(flags), ni, nj, nk,
+            sp_in.ctypes.data, sp_out.ctypes.data, int(bool(affine_first)), int(mode),
+            _ptr(fill), _stream(src),
+        )
+    _count(1)
+    return dst
+
+
+def min_sample0(src: Tensor) -> Tensor:
+    """Per-channel min of batch element 0, on device, no sync
+    (spatial/spatial.py:2054-2060,2094-2095)."""
+    _require_cuda(src, "min_sample0")
+    src = src.contiguous()
+    c = src.shape[1]
+    n = src[0, 0].numel()
+    fill = torch.empty(c, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _native.call("tio_min_sample0", _ptr(src), c, n, _ptr(fill), _stream(src))
+    _count(2)
+    return fill
+
+
+def bias_field(src: Tensor, coarse: Tensor, identity: Tensor | None, *, divide=False,
+               out: Tensor | None = None) -> Tensor:
+    """K2 (intensity/bias_field.py:201-255,296-341)."""
+    _require_cuda(src, "bias_field")
+    src = src.contiguous()
+    b, c, i, j, k = src.shape
+    dst = torch.empty_like(src) if out is None else out
+    si, sj, sk = coarse.shape[2:]
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_bias_field", _ptr(src), _ptr(dst), b, c, i, j, k, _ptr(coarse), si, sj, sk,
+            _ptr(identity), int(bool(divide)), _stream(src),
+        )
+    _count(1)
+    return dst
+
+
+def blur(src: Tensor, taps: Tensor, radius: Tensor, big_r: int, axes_mask: int,
+         identity: Tensor | None) -> Tensor:
+    """K3 (intensity/blur.py:129-252)."""
+    _require_cuda(src, "blur")
+    src = src.contiguous()
+    b, c, i, j, k = src.shape
+    dst = torch.empty_like(src)
+    n_axes = bin(axes_mask & 7).count("1")
+    scratch = torch.empty_like(src) if n_axes >= 2 else None
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_blur", _ptr(src), _ptr(dst), _ptr(scratch), b, c, i, j, k, _ptr(taps),
+            _ptr(radius), int(big_r), int(axes_mask), _ptr(identity), _stream(src),
+        )
+    _count(max(n_axes, 1))
+    return dst
+
+
+def noise(src: Tensor, mean: Tensor, std: Tensor, keep: Tensor | None, z: Tensor,
+          z2: Tensor | None = None) -> Tensor:
+    """K4 with caller-provided normals (intensity/noise.py:98-178)."""
+    _require_cuda(src, "noise")
+    src = src.contiguous()
+    dst = torch.empty_like(src)
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_noise", _ptr(src), _ptr(dst), src.shape[0], src[0].numel(), _ptr(mean),
+            _ptr(std), _ptr(keep), _ptr(z), _ptr(z2), _stream(src),
+        )
+    _count(1)
+    return dst
+
+
+def noise_philox(src: Tensor, mean: Tensor, std: Tensor, keep: Tensor | None, seed: int,
+                 rician: bool = False) -> Tensor:
+    """K4b: in-register Philox normals (not the reference stream)."""
+    _require_cuda(src, "noise_philox")
+    src = src.contiguous()
+    dst = torch.empty_like(src)
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_noise_philox", _ptr(src), _ptr(dst), src.shape[0], src[0].numel(),
+            _ptr(mean), _ptr(std), _ptr(keep), int(seed), int(bool(rician)), _stream(src),
+        )
+    _count(1)
+    return dst
+
+
+def gamma(src: Tensor, gam: Tensor) -> Tensor:
+    """K5 (intensity/gamma.py:88-90)."""
+    _require_cuda(src, "gamma")
+    src = src.contiguous()
+    dst = torch.empty_like(src)
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_gamma", _ptr(src), _ptr(dst), src.shape[0], src[0].numel(), _ptr(gam),
+            _stream(src),
+        )
+    _count(1)
+    return dst

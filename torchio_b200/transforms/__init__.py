@@ -1,0 +1,13 @@
+from .base import (AppliedTransform, IntensityTransform, SpatialTransform, Transform,
+                   execution_device, set_execution_device)
+from .compose import Compose
+from .intensity import BiasField, Blur, Gamma, Noise
+from .inverse import apply_inverse_transform, get_inverse_transform
+from .spatial import Affine, ElasticDeformation, Spatial
+
+__all__ = [
+    "Affine", "AppliedTransform", "BiasField", "Blur", "Compose", "ElasticDeformation",
+    "Gamma", "IntensityTransform", "Noise", "Spatial", "SpatialTransform", "Transform",
+    "apply_inverse_transform", "execution_device", "get_inverse_transform",
+    "set_execution_device",
+]

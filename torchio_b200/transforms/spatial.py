@@ -1,0 +1,574 @@
+"""Spatial / Affine / ElasticDeformation behind the reference API.
+
+Host-side mirror of transforms/spatial/spatial.py (TorchIO 2.0.0a2):
+constructor signatures, validation messages, ``make_params`` RNG order and the
+``params`` schema are the reference's (spatial.py:307-369, 436-558,
+2219-2375, 2427-2484); ``apply_transform`` packs the sampled geometry into
+three small tables and runs ONE fused CUDA pass per image
+(`ops.resample`, K1) instead of materialising a sampling grid and calling
+``grid_sample`` twice (spatial.py:1110-1272, 1504-1857).
+
+Supported natively: interpolation orders 0-1 (``"nearest"``/``"linear"``),
+``target=None`` or a concrete ``(shape, affine)`` space, fills ``"minimum"``,
+``"mean"`` or numeric.  Out of scope this round (raise NotImplementedError):
+B-spline orders >= 2, ``label_interpolation="label"``, ``antialias``,
+``default_pad_value="otsu"``, random/path/str targets.
+"""
+
+from __future__ import annotations
+
+import threading
+import warnings
+from numbers import Number
+from typing import Any
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.distributions import Distribution
+
+from .. import ops, tables
+from ..data import AffineMatrix, Image, ImagesBatch, LabelMap, SubjectsBatch
+from ..params import Choice, _ParameterRange
+from .base import SpatialTransform
+
+_ORDERS = {
+    "nearest": 0, "linear": 1, "quadratic": 2, "cubic": 3,
+    "fourth": 4, "fifth": 5, "sixth": 6, "seventh": 7,
+}
+_NAMES = {v: k for k, v in _ORDERS.items()}
+LABEL_INTERPOLATION = "label"
+_PAD_MODES = ("minimum", "mean", "otsu")
+_SPLINE_ORDER = 3
+
+_packed = threading.local()  # make_params -> apply_transform hand-off (per thread)
+
+
+# ---- argument parsing (messages follow spatial.py:2592-2762) -----------------
+
+
+def _range(value) -> _ParameterRange:
+    if isinstance(value, (Distribution, Choice)):
+        return _ParameterRange(value)
+    if isinstance(value, (int, float)):
+        return _ParameterRange(float(value))
+    if isinstance(value, tuple) and all(isinstance(v, (int, float)) for v in value):
+        return _ParameterRange(tuple(float(v) for v in value))
+    return _ParameterRange(value)
+
+
+def _positive_range(value) -> _ParameterRange:
+    r = _range(value)
+    if r._distribution is None and any(lo <= 0 or hi <= 0 for lo, hi in r._ranges):
+        raise ValueError(f"Scale factors must be strictly positive, got {value}")
+    return r
+
+
+def _nonnegative_range(value) -> _ParameterRange:
+    r = _range(value)
+    if r._distribution is None and any(lo < 0 or hi < 0 for lo, hi in r._ranges):
+        raise ValueError(f"Value must be non-negative, got {value}")
+    return r
+
+
+def _interpolation(value) -> str:
+    if isinstance(value, int) and not isinstance(value, bool):
+        if value not in _NAMES:
+            raise ValueError(f"Interpolation order {value} is not supported. Must be 0-7.")
+        return _NAMES[value]
+    if not isinstance(value, str):
+        raise TypeError(f"Interpolation must be a string or int, got {type(value)}")
+    lowered = value.lower()
+    supported = (*_ORDERS, LABEL_INTERPOLATION)
+    if lowered not in supported:
+        raise ValueError(
+            f'Interpolation "{lowered}" is not supported. Supported values are {supported}'
+        )
+    return lowered
+
+
+def _control_points(value) -> Tensor:
+    t = (
+        value.clone().detach().to(torch.float32)
+        if isinstance(value, Tensor)
+        else torch.as_tensor(np.asarray(value), dtype=torch.float32)
+    )
+    if t.ndim != 4 or t.shape[-1] != 3:
+        raise ValueError(
+            f"control_points must have shape (n_i, n_j, n_k, 3), got {tuple(t.shape)}"
+        )
+    for axis, size in enumerate(t.shape[:-1]):
+        if size < 4:
+            raise ValueError(
+                "Each control-point axis must have at least 4 elements;"
+                f" axis {axis} got {size}"
+            )
+    return t.contiguous()
+
+
+def _max_abs(cp: Tensor) -> tuple[float, float, float]:
+    a = cp.abs()
+    return (float(a[..., 0].max()), float(a[..., 1].max()), float(a[..., 2].max()))
+
+
+# ---- geometry (float64 host math, spatial.py:2269-2375) ------------------------
+
+
+def _rotation(degrees: np.ndarray) -> np.ndarray:
+    rx, ry, rz = np.radians(degrees)
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    mx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]], dtype=np.float64)
+    my = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]], dtype=np.float64)
+    mz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]], dtype=np.float64)
+    return mz @ my @ mx
+
+
+def build_forward_affine(scales, degrees, translation, center: str, shape, affine) -> np.ndarray:
+    """World-space T = [R S | c - R S c + t], pivot at the image centre."""
+    scaling = np.asarray(scales, dtype=np.float64)
+    rotation = np.asarray(degrees, dtype=np.float64)
+    shift = np.asarray(translation, dtype=np.float64)
+    if shape[-1] == 1:  # 2-D input: suppress out-of-plane terms
+        scaling[2] = 1.0
+        rotation[0] = rotation[1] = 0.0
+        shift[2] = 0.0
+    rs = _rotation(rotation) @ np.diag(scaling)
+    t = np.eye(4, dtype=np.float64)
+    t[:3, :3] = rs
+    if center == "image":
+        m = affine.numpy()
+        c = m[:3, 3] + m[:3, :3] @ ((np.asarray(shape, dtype=np.float64) - 1) / 2)
+        t[:3, 3] = c - rs @ c
+    t[:3, 3] += shift
+    return t
+
+
+def _sample_control_points(grid_shape, max_displacement, locked_borders: int) -> Tensor:
+    """U(-max, +max) per axis, outer shells zeroed (spatial.py:2241-2266)."""
+    field = torch.rand(*grid_shape, 3, dtype=torch.float32)
+    field -= 0.5
+    field *= 2
+    for axis in range(3):
+        field[..., axis] *= max_displacement[axis]
+    for border in range(locked_borders):
+        field[border, :] = 0
+        field[-1 - border, :] = 0
+        field[:, border] = 0
+        field[:, -1 - border] = 0
+        field[:, :, border] = 0
+        field[:, :, -1 - border] = 0
+    return field
+
+
+def _check_folding(cp_shape, max_displacement, shape, spacing) -> None:
+    """RuntimeWarning heuristic of spatial.py:2192-2216."""
+    mesh = np.asarray(cp_shape, dtype=np.float64) - _SPLINE_ORDER
+    grid_spacing = np.asarray(shape, dtype=np.float64) * spacing / mesh
+    conflicts = np.asarray(max_displacement, dtype=np.float64) > grid_spacing / 2
+    if np.any(conflicts):
+        (where,) = np.where(conflicts)
+        warnings.warn(
+            "The maximum displacement is larger than half the coarse-grid spacing for"
+            f" dimensions {where.tolist()}, so folding may occur",
+            RuntimeWarning,
+            stacklevel=4,
+        )
+
+
+def _shape_of(ib: ImagesBatch) -> tuple[int, int, int]:
+    s = ib.data.shape
+    return (int(s[-3]), int(s[-2]), int(s[-1]))
+
+
+def _check_shared_space(images, shape, affine: AffineMatrix) -> None:
+    ref = affine.numpy()
+    for name, ib in images.items():
+        if _shape_of(ib) != shape:
+            raise RuntimeError(f'Image "{name}" has shape {_shape_of(ib)}, expected {shape}')
+        for a in ib.affines:
+            if not np.allclose(a.numpy(), ref, rtol=1e-6, atol=1e-6):
+                raise RuntimeError(
+                    "Spatial transforms with affine or elastic components require"
+                    " selected images to share the same affine"
+                )
+
+
+def _space_to_json(space):
+    if space is None:
+        return None
+    shape, affine = space
+    return {"shape": list(shape), "affine": affine.numpy().tolist()}
+
+
+def _space_from_json(d):
+    if d is None:
+        return None
+    s = d["shape"]
+    return (int(s[0]), int(s[1]), int(s[2])), AffineMatrix(np.asarray(d["affine"], dtype=np.float64))
+
+
+def _resolve_target(target, batch, shape, affine):
+    if target is None:
+        return None
+    if isinstance(target, Image):
+        return tuple(target.spatial_shape), target.affine.clone()
+    if isinstance(target, tuple) and len(target) == 2 and not isinstance(target[0], Number):
+        s, a = target
+        if len(s) != 3:
+            raise ValueError(f"Target shape must have length 3, got {len(s)}")
+        return (int(s[0]), int(s[1]), int(s[2])), AffineMatrix(a)
+    raise NotImplementedError(
+        "torchio_b200.Spatial supports target=None, an Image or a (shape, affine) pair;"
+        " spacing / random / named targets are not implemented yet"
+    )
+
+
+# ---- the transform -----------------------------------------------------------
+
+
+class Spatial(SpatialTransform):
+    """Resample + affine + elastic in one fused pass (spatial.py:158-369)."""
+
+    def __init__(self, *, target=None, scales=1.0, degrees=0.0, translation=0.0,
+                 isotropic: bool = False, center: str = "image", control_points=None,
+                 num_control_points=7, max_displacement=0.0, locked_borders: int = 2,
+                 affine_first: bool = True, image_interpolation="linear",
+                 label_interpolation="nearest", one_hot_label_interpolation="linear",
+                 antialias: bool = False, default_pad_value="minimum",
+                 default_pad_label=0, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.target = target
+        if isotropic and not isinstance(scales, Distribution):
+            if isinstance(scales, tuple) and len(scales) in (3, 6):
+                raise ValueError(
+                    "If isotropic=True, scales must be a single value or a 2-value range"
+                )
+        self.scales = _positive_range(scales)
+        self.degrees = _range(degrees)
+        self.translation = _range(translation)
+        self.isotropic = isotropic
+        if center not in ("image", "origin"):
+            raise ValueError(f'center must be "image" or "origin", got "{center}"')
+        self.center = center
+        self.control_points = None if control_points is None else _control_points(control_points)
+        ncp = (num_control_points,) * 3 if isinstance(num_control_points, int) else num_control_points
+        for axis, number in enumerate(ncp):
+            if not isinstance(number, int) or number < 4:
+                raise ValueError(
+                    "Each num_control_points value must be an integer greater than 3;"
+                    f" axis {axis} got {number}"
+                )
+        self.num_control_points = tuple(ncp)
+        self.max_displacement = _nonnegative_range(max_displacement)
+        if locked_borders not in (0, 1, 2):
+            raise ValueError(f"locked_borders must be 0, 1, or 2, got {locked_borders}")
+        self.locked_borders = locked_borders
+        if self.locked_borders == 2 and 4 in self.num_control_points:
+            raise ValueError(
+                "locked_borders=2 with 4 control points along any axis yields an"
+                " identity elastic field"
+            )
+        self.affine_first = affine_first
+        image_interpolation = _interpolation(image_interpolation)
+        if image_interpolation == LABEL_INTERPOLATION:
+            raise ValueError(
+                f'image_interpolation cannot be "{LABEL_INTERPOLATION}"; that mode'
+                " is only valid for label_interpolation"
+            )
+        self.image_interpolation = image_interpolation
+        self.label_interpolation = _interpolation(label_interpolation)
+        one_hot = _interpolation(one_hot_label_interpolation)
+        if one_hot == LABEL_INTERPOLATION:
+            raise ValueError(
+                f'one_hot_label_interpolation cannot be "{LABEL_INTERPOLATION}"; choose'
+                ' an interpolation for the one-hot channels (e.g. "linear")'
+            )
+        self.one_hot_label_interpolation = one_hot
+        self.antialias = antialias
+        if isinstance(default_pad_value, Number):
+            default_pad_value = float(default_pad_value)
+        elif default_pad_value not in _PAD_MODES:
+            raise ValueError(
+                'default_pad_value must be "minimum", "mean", "otsu", or a numeric value'
+            )
+        self.default_pad_value = default_pad_value
+        if not isinstance(default_pad_label, Number):
+            raise TypeError(f"default_pad_label must be numeric, got {type(default_pad_label)}")
+        self.default_pad_label = float(default_pad_label)
+
+    @property
+    def supports_per_instance_params(self) -> bool:
+        return True
+
+    @property
+    def supports_per_instance_p(self) -> bool:
+        return self.target is None
+
+    # -- sampling (RNG order: SURVEY.md Appendix B) ---------------------------
+
+    def _sample_one(self, shape, affine: AffineMatrix):
+        if self.isotropic:
+            v = self.scales.sample_1d()
+            scales = (v, v, v)
+        else:
+            scales = self.scales.sample()
+        degrees = self.degrees.sample()
+        translation = self.translation.sample()
+        has_affine = not (
+            np.allclose(scales, (1.0, 1.0, 1.0))
+            and np.allclose(degrees, (0.0, 0.0, 0.0))
+            and np.allclose(translation, (0.0, 0.0, 0.0))
+        )
+        if self.control_points is not None:
+            cp, max_disp = self.control_points.clone(), _max_abs(self.control_points)
+        else:
+            max_disp = self.max_displacement.sample()
+            if all(v == 0.0 for v in max_disp):
+                cp, max_disp = None, None
+            else:
+                cp = _sample_control_points(self.num_control_points, max_disp, self.locked_borders)
+        forward = None
+        if has_affine:
+            forward = build_forward_affine(scales, degrees, translation, self.center, shape, affine)
+        return forward, cp, max_disp
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        images = self._get_images(batch)
+        if not images:
+            return {"selected_images": []}
+        first = next(iter(images.values()))
+        shape, affine = _shape_of(first), first.affines[0]
+        params: dict[str, Any] = {
+            "selected_images": list(images),
+            "original": _space_to_json((shape, affine)),
+            "affine_first": self.affine_first,
+            "image_interpolation": self.image_interpolation,
+            "label_interpolation": self.label_interpolation,
+            "one_hot_label_interpolation": self.one_hot_label_interpolation,
+            "antialias": self.antialias,
+            "default_pad_value": self.default_pad_value,
+            "default_pad_label": self.default_pad_label,
+        }
+        n = self._resolve_n(batch)
+        if n is None:
+            forward, cp, max_disp = self._sample_one(shape, affine)
+            if forward is not None or cp is not None:
+                _check_shared_space(images, shape, affine)
+            params["target"] = _space_to_json(_resolve_target(self.target, batch, shape, affine))
+            params["affine_matrix"] = None if forward is None else forward.tolist()
+            params["control_points"] = None if cp is None else cp.tolist()
+            params["max_displacement"] = list(max_disp) if max_disp else None
+            _packed.entry = (params, ([forward], [None if cp is None else cp.numpy()], False))
+            return params
+        keep = self._keep_mask(batch, n)
+        forwards, cps, disps = [], [], []
+        for index in range(n):
+            if keep is not None and not bool(keep[index]):
+                forwards.append(None); cps.append(None); disps.append(None)
+                continue
+            forward, cp, max_disp = self._sample_one(shape, affine)
+            forwards.append(forward)
+            cps.append(None if cp is None else cp.numpy())
+            disps.append(list(max_disp) if max_disp else None)
+        if any(f is not None for f in forwards) or any(c is not None for c in cps):
+            _check_shared_space(images, shape, affine)
+        params["target"] = _space_to_json(_resolve_target(self.target, batch, shape, affine))
+        params["affine_matrix"] = [None if f is None else f.tolist() for f in forwards]
+        params["control_points"] = [None if c is None else c.tolist() for c in cps]
+        params["max_displacement"] = disps
+        self._tag_batched(params, batch, n, keep,
+                          ["affine_matrix", "control_points", "max_displacement"])
+        _packed.entry = (params, (forwards, cps, True))
+        return params
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        names = params.get("selected_images", [])
+        if not names:
+            return batch
+        geometry = _unpack_geometry(params)
+        disps = params["max_displacement"]
+        if not geometry[2]:
+            disps = [disps]
+        _apply_spatial(
+            batch, names, _space_from_json(params["target"]), geometry, max_displacements=disps,
+            affine_first=params["affine_first"],
+            image_interpolation=params["image_interpolation"],
+            label_interpolation=params["label_interpolation"],
+            antialias=params.get("antialias", False),
+            default_pad_value=params["default_pad_value"],
+            default_pad_label=float(params["default_pad_label"]),
+        )
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]) -> _SpatialInverse:
+        """Exact inverse affine, negated elastic field, flipped order, original
+        grid as target (spatial.py:617-676, 925-959)."""
+        original = _space_from_json(params["original"])
+        if original is None:
+            raise RuntimeError("Spatial inverse needs the original output space")
+        mats, cps, per_instance = _unpack_geometry(params)
+        inv_mats = [None if m is None else np.linalg.inv(np.asarray(m, dtype=np.float64))
+                    for m in mats]
+        inv_cps = [None if c is None else -np.asarray(c, dtype=np.float32) for c in cps]
+        return _SpatialInverse(
+            target=original, geometry=(inv_mats, inv_cps, per_instance),
+            affine_first=not params["affine_first"],
+            image_interpolation=params["image_interpolation"],
+            label_interpolation=params["label_interpolation"],
+            default_pad_value=params["default_pad_value"],
+            default_pad_label=float(params["default_pad_label"]),
+            copy=False, include=params["selected_images"],
+        )
+
+
+def _unpack_geometry(params):
+    """(affine matrices, control grids, per_instance) as numpy, reusing the
+    arrays make_params just produced when ``params`` is that very dict."""
+    entry = getattr(_packed, "entry", None)
+    if entry is not None and entry[0] is params:
+        return entry[1]
+    per_instance = "affine_matrix" in (params.get("_batched_keys") or [])
+    mats, cps = params["affine_matrix"], params["control_points"]
+    if not per_instance:
+        mats, cps = [mats], [cps]
+    mats = [None if m is None else np.asarray(m, dtype=np.float64) for m in mats]
+    cps = [None if c is None else np.asarray(c, dtype=np.float32) for c in cps]
+    return mats, cps, per_instance
+
+
+class _SpatialInverse(SpatialTransform):
+    """Concrete inverse used by history replay (spatial.py:679-756)."""
+
+    def __init__(self, *, target, geometry, affine_first, image_interpolation,
+                 label_interpolation, default_pad_value, default_pad_label, **kwargs: Any):
+        super().__init__(**kwargs)
+        self.target = target
+        self.geometry = geometry
+        self.affine_first = affine_first
+        self.image_interpolation = image_interpolation
+        self.label_interpolation = label_interpolation
+        self.default_pad_value = default_pad_value
+        self.default_pad_label = float(default_pad_label)
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        _apply_spatial(
+            batch, list(self._get_images(batch)), self.target, self.geometry,
+            affine_first=self.affine_first, image_interpolation=self.image_interpolation,
+            label_interpolation=self.label_interpolation, antialias=False,
+            default_pad_value=self.default_pad_value, default_pad_label=self.default_pad_label,
+        )
+        return batch
+
+
+def _fill_tensor(data: Tensor, is_label: bool, pad_value, pad_label):
+    """Device (C,) fill or None (= skip the mask step, only for a python-float
+    0.0; spatial.py:2034-2086)."""
+    c = data.shape[1]
+    if is_label:
+        value = float(pad_label)
+    elif isinstance(pad_value, Number):
+        value = float(pad_value)
+    elif pad_value == "minimum":  # sample 0, per channel, no host sync
+        first = data[:1]
+        return ops.min_sample0(first if first.dtype == torch.float32 else first.float())
+    elif pad_value == "mean":  # mean of the six border faces of sample 0
+        x = data[0]
+        faces = [x[:, 0], x[:, -1], x[:, :, 0], x[:, :, -1], x[:, :, :, 0], x[:, :, :, -1]]
+        return torch.cat([f.reshape(c, -1) for f in faces], dim=1).float().mean(dim=1)
+    else:
+        raise NotImplementedError('default_pad_value="otsu" is not implemented in torchio_b200')
+    if value == 0.0:
+        return None
+    return torch.full((c,), value, dtype=torch.float32, device=data.device)
+
+
+def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_interpolation,
+                   label_interpolation, antialias, default_pad_value, default_pad_label,
+                   max_displacements=None) -> None:
+    if not names:
+        return
+    if antialias:
+        raise NotImplementedError("antialias=True is not implemented in torchio_b200")
+    mats, cps, per_instance = geometry
+    first = batch.images[names[0]]
+    in_shape, a_in = _shape_of(first), first.affines[0]
+    out_shape, a_out = (in_shape, a_in) if target_space is None else target_space
+    b = first.batch_size
+    packed = tables.spatial_tables(
+        mats if per_instance else mats[0], cps if per_instance else cps[0], b,
+        a_in.numpy(), a_out.numpy(), per_instance=per_instance,
+        has_target=target_space is not None,
+    )
+    if packed is None:  # exact no-op: data and affines untouched (spatial.py:579-590)
+        return
+    sp_out = np.asarray(a_out.spacing, dtype=np.float64)
+    for index, cp in enumerate(cps):
+        if cp is None:
+            continue
+        disp = max_displacements[index] if max_displacements else None
+        if disp is None:
+            disp = np.abs(cp).reshape(-1, 3).max(axis=0)
+        _check_folding(cp.shape[:3], disp, out_shape, sp_out)
+    device = first.data.device
+    mat_d, cp_d, flags_d = ops.upload(device, packed.mat, packed.cp, packed.flags)
+    for name in names:
+        ib = batch.images[name]
+        is_label = issubclass(ib._image_class, LabelMap)
+        interp = label_interpolation if is_label else image_interpolation
+        if interp not in ("nearest", "linear"):
+            raise NotImplementedError(
+                f'interpolation "{interp}" is not implemented in torchio_b200 (orders 0-1 only)'
+            )
+        data = ib.data
+        native = data if data.dtype in ops.DTYPE_CODES else data.float()
+        fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
+        out = ops.resample(
+            native, mat_d, cp_d, flags_d, a_in.spacing, a_out.spacing,
+            affine_first=affine_first, mode=ops.NEAREST if interp == "nearest" else ops.LINEAR,
+            fill=fill, out_shape=None if target_space is None else out_shape,
+        )
+        ib.data = out if out.dtype == data.dtype else out.to(data.dtype)
+        keep_original = set(packed.passthrough)
+        ib.affines[:] = [
+            ib.affines[i] if i in keep_original else a_out.clone() for i in range(b)
+        ]
+
+
+class Affine(Spatial):
+    """Affine-only wrapper (spatial.py:806-869)."""
+
+    def __init__(self, *, scales=1.0, degrees=0.0, translation=0.0, isotropic: bool = False,
+                 center: str = "image", default_pad_value="minimum", default_pad_label=0,
+                 image_interpolation="linear", label_interpolation="nearest",
+                 one_hot_label_interpolation="linear", **kwargs: Any) -> None:
+        super().__init__(
+            scales=scales, degrees=degrees, translation=translation, isotropic=isotropic,
+            center=center, default_pad_value=default_pad_value,
+            default_pad_label=default_pad_label, image_interpolation=image_interpolation,
+            label_interpolation=label_interpolation,
+            one_hot_label_interpolation=one_hot_label_interpolation, **kwargs,
+        )
+        self._warn_if_noop(
+            is_noop=self.scales.is_constant(1.0) and self.degrees.is_constant(0.0)
+            and self.translation.is_constant(0.0),
+            hint="degrees=(-15, 15)",
+        )
+
+
+class ElasticDeformation(Spatial):
+    """Elastic-only wrapper (spatial.py:872-922)."""
+
+    def __init__(self, *, control_points=None, num_control_points=7, max_displacement=7.5,
+                 locked_borders: int = 2, image_interpolation="linear",
+                 label_interpolation="nearest", one_hot_label_interpolation="linear",
+                 **kwargs: Any) -> None:
+        super().__init__(
+            control_points=control_points, num_control_points=num_control_points,
+            max_displacement=max_displacement, locked_borders=locked_borders,
+            image_interpolation=image_interpolation, label_interpolation=label_interpolation,
+            one_hot_label_interpolation=one_hot_label_interpolation, **kwargs,
+        )
