@@ -116,8 +116,8 @@ int tio_bias_field(const float* src, float* dst, int B, int C, int I, int J, int
  *   axes_mask host int, bit a set = axis a is active for at least one element
  *             (lets the library skip whole passes without reading `radius`)
  *   identity  [B] bytes: rows with all sigma <= 0 are copied exactly
- *   scratch   device buffer of B*C*I*J*K floats (may be NULL if at most one
- *             axis is active for every element)
+ *   scratch   device buffer of B*C*I*J*K floats (may be NULL when only the I
+ *             axis is active)
  * src and dst must not alias.
  */
 int tio_blur(const float* src, float* dst, float* scratch,
@@ -155,6 +155,32 @@ int tio_noise_philox(const float* src, float* dst, int B, int64_t per_elem,
  */
 int tio_gamma(const float* src, float* dst, int B, int64_t per_elem,
               const float* gamma, void* stream);
+
+/*
+ * Fused intensity chain: what Compose([BiasField, Blur, Noise, Gamma]) computes,
+ * in two HBM passes.  Any stage may be absent (NULL table / noise_mode 0):
+ *   v   = src * exp(trilerp(coarse))   (/ when bias_divide)  if coarse != NULL
+ *   v   = blur_I(blur_J(blur_K(v)))                          if taps   != NULL
+ *   v   = v + mean[b] + std[b] * n  (or Rician)               if noise_mode != 0
+ *   dst = sign(v) |v|^gamma[b]                                if gamma  != NULL
+ * Equal to running K2, K3, K4, K5 one after another up to fp32 summation order
+ * (the separable passes commute; the reference order is I, J, K).
+ *   noise_mode 1: normals supplied in z (z2 for the second Rician draw)
+ *   noise_mode 2: Philox4x32-10 keyed by philox_seed (NOT the reference stream)
+ *   per-element identity rows (bias_identity[b], all radii 0, keep[b] == 0,
+ *   gamma[b] == 1) pass through every stage as bit-exact copies
+ *   scratch: B*C*I*J*K floats, required when axes_mask has bit 1 or 2 (J/K)
+ * src, dst, scratch must be distinct when blur is active.
+ */
+int tio_intensity_fused(const float* src, float* dst, float* scratch,
+                        int B, int C, int I, int J, int K,
+                        const float* coarse, int si, int sj, int sk,
+                        const uint8_t* bias_identity, int bias_divide,
+                        const float* taps, const int32_t* radius, int R, int axes_mask,
+                        const float* mean, const float* std, const uint8_t* keep,
+                        const float* z, const float* z2,
+                        uint64_t philox_seed, int noise_mode, int rician,
+                        const float* gamma, void* stream);
 
 #ifdef __cplusplus
 }

@@ -189,3 +189,93 @@ def test_philox_noise_statistics():
     assert not torch.equal(y, y3)
     kurt = float(((y[0] - y[0].mean()) ** 4).mean() / y[0].var() ** 2)
     assert abs(kurt - 3.0) < 0.05
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 40, 36, 64), (3, 2, 19, 33, 70), (2, 1, 9, 7, 5),
+                                   (1, 1, 24, 20, 1), (2, 1, 70, 40, 132)])
+@pytest.mark.parametrize("sigma_max", [1.9, 4.5])
+def test_fused_chain_equals_sequential_kernels(shape, sigma_max):
+    """tio_intensity_fused == bias -> blur -> noise -> gamma one after another
+    (C oracle), for vector and scalar paths, radii up to 14, ragged tiles."""
+    from torchio_b200 import ops, tables
+
+    c_port = _orc()
+    p = c_port._p
+    lib = c_port.lib()
+    b, c = shape[:2]
+    g = torch.Generator().manual_seed(17)
+    rng = np.random.default_rng(17)
+    x = torch.rand(shape, generator=g) - 0.2
+    n = x[0].numel()
+    coarse = torch.randn((b, c, 4, 5, 6), generator=g) * 0.4
+    bias_ident = torch.zeros(b, dtype=torch.uint8)
+    sig = rng.uniform(0.0, sigma_max, (b, 3))
+    sig[:, 2] = np.where(shape[4] == 1, 0.0, sig[:, 2])
+    if b > 1:
+        sig[1] = 0.0  # one identity row
+        bias_ident[1] = 1
+    t = tables.blur_tables(sig, b)
+    z = torch.randn(shape, generator=g)
+    mean = torch.tensor(rng.uniform(-0.1, 0.1, b), dtype=torch.float32)
+    std = torch.tensor(rng.uniform(0.0, 0.3, b), dtype=torch.float32)
+    keep = torch.ones(b, dtype=torch.uint8)
+    gam = torch.tensor(np.exp(rng.uniform(-0.3, 0.3, b)), dtype=torch.float32)
+    if b > 1:
+        keep[1] = 0
+        gam[1] = 1.0
+    # oracle chain
+    s1, s2, s3, s4 = (torch.empty_like(x) for _ in range(4))
+    lib.orc_bias_field(p(x), p(s1), b, c, *shape[2:], p(coarse), 4, 5, 6, p(bias_ident), 0)
+    lib.orc_blur(p(s1), p(s2), None, b, c, *shape[2:], p(t.taps), p(t.radius), t.big_r, p(t.identity))
+    lib.orc_noise(p(s2), p(s3), b, ctypes.c_int64(n), p(mean), p(std), p(keep), p(z), None)
+    lib.orc_gamma(p(s3), p(s4), b, ctypes.c_int64(n), p(gam))
+    dev = "cuda"
+    got = ops.intensity_fused(
+        x.to(dev), coarse=coarse.to(dev), bias_identity=bias_ident.to(dev),
+        taps=t.taps.to(dev), radius=t.radius.to(dev), big_r=t.big_r, axes_mask=t.axes_mask,
+        mean=mean.to(dev), std=std.to(dev), keep=keep.to(dev), z=z.to(dev), noise_mode=1,
+        gamma=gam.to(dev),
+    ).cpu()
+    rngv = float(s4.max() - s4.min())
+    assert float((got - s4).abs().max()) <= 3e-6 * rngv
+    if b > 1:
+        assert torch.equal(got[1], x[1])  # fully gated row: bit-exact copy
+    # blur alone through the same kernels
+    got_b = ops.blur(x.to(dev), t.taps.to(dev), t.radius.to(dev), t.big_r, t.axes_mask,
+                     t.identity.to(dev)).cpu()
+    want_b = torch.empty_like(x)
+    lib.orc_blur(p(x), p(want_b), None, b, c, *shape[2:], p(t.taps), p(t.radius), t.big_r, p(t.identity))
+    assert float((got_b - want_b).abs().max()) <= 2e-6
+
+
+def test_fused_compose_equals_unfused_compose():
+    import warnings
+
+    import torchio_b200 as tio
+
+    subjects = []
+    for b in range(3):
+        gsub = torch.Generator().manual_seed(50 + b)
+        subjects.append(tio.Subject(t1=tio.ScalarImage(torch.rand((1, 40, 36, 32), generator=gsub)),
+                                    seg=tio.LabelMap(torch.zeros((1, 40, 36, 32), dtype=torch.int16))))
+    outs = []
+    for fuse in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pipe = tio.Compose([tio.BiasField(), tio.Blur(std=(0, 2)), tio.Noise(std=(0, 0.25)),
+                                tio.Gamma(log_gamma=(-0.3, 0.3))])
+        pipe.fuse = fuse
+        torch.manual_seed(5)
+        out = pipe(tio.SubjectsBatch.from_subjects(subjects).to("cuda"))
+        assert [t.name for t in out.applied_transforms] == ["BiasField", "Blur", "Noise", "Gamma"]
+        outs.append(out)
+    a, b = outs[0].images["t1"].data, outs[1].images["t1"].data
+    assert float((a - b).abs().max()) <= 3e-6 * float(b.max() - b.min())
+    assert json_equal(outs[0].applied_transforms, outs[1].applied_transforms)
+
+
+def json_equal(h1, h2):
+    import json
+
+    f = lambda h: json.dumps([{"name": t.name, "params": t.params} for t in h], sort_keys=True)
+    return f(h1) == f(h2)

@@ -29,6 +29,10 @@ _SIGNATURES = {
     "tio_noise_philox": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                          c_uint64, c_int, c_void_p],
     "tio_gamma": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p],
+    "tio_intensity_fused": [c_void_p, c_void_p, c_void_p] + [c_int] * 5
+    + [c_void_p, c_int, c_int, c_int, c_void_p, c_int]
+    + [c_void_p, c_void_p, c_int, c_int]
+    + [c_void_p] * 5 + [c_uint64, c_int, c_int, c_void_p, c_void_p],
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 // All kernels are HBM-bound elementwise / stencil passes: 128-bit accesses
 // along K, grid sized to the volume, no tensor cores.
 #include "common.cuh"
+#include "intensity_common.cuh"
 
 namespace tio {
 
@@ -94,49 +95,8 @@ bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int I
 }
 
 // ---------------------------------------------------------------------------
-// K3 (v1): one kernel per active axis, replicate (clamp) addressing.
-// ---------------------------------------------------------------------------
-template <int AXIS>
-__global__ void __launch_bounds__(256)
-blur_axis_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int I, int J,
-                 int K, const float* __restrict__ taps, const int32_t* __restrict__ radius,
-                 int B, int R) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jt = (J + blockDim.y - 1) / blockDim.y;
-  const int j = (blockIdx.y % jt) * blockDim.y + threadIdx.y;
-  const int i = blockIdx.y / jt;
-  const int bc = blockIdx.z;
-  if (k >= K || j >= J) return;
-  const int b = bc / C;
-  const int64_t n = (int64_t)I * J * K;
-  const float* x = src + (int64_t)bc * n;
-  const int64_t o = ((int64_t)i * J + j) * K + k;
-  const int r = radius[AXIS * B + b];
-  if (r <= 0) {
-    dst[(int64_t)bc * n + o] = x[o];
-    return;
-  }
-  const float* t = taps + ((int64_t)AXIS * B + b) * (2 * R + 1) + R;
-  const int pos = AXIS == 0 ? i : (AXIS == 1 ? j : k);
-  const int len = AXIS == 0 ? I : (AXIS == 1 ? J : K);
-  const int64_t stride = AXIS == 0 ? (int64_t)J * K : (AXIS == 1 ? K : 1);
-  const int64_t base = o - (int64_t)pos * stride;
-  float acc = 0.0f;
-  for (int d = -r; d <= r; ++d) {
-    int q = min(max(pos + d, 0), len - 1);
-    acc = __fmaf_rn(__ldg(t + d), __ldg(x + base + (int64_t)q * stride), acc);
-  }
-  dst[(int64_t)bc * n + o] = acc;
-}
-
-// ---------------------------------------------------------------------------
 // K4: noise (given normals) / Philox variant;  K5: gamma
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float rician(float x, float n1, float n2) {
-  float s = __fadd_rn(x, n1);
-  return sqrtf(__fadd_rn(__fmul_rn(s, s), __fmul_rn(n2, n2)));
-}
-
 template <int V, bool RICIAN>
 __global__ void __launch_bounds__(256)
 noise_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t per_elem,
@@ -179,30 +139,6 @@ noise_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t per
     if (V == 4) *(float4*)(dst + o) = make_float4(yv[0], yv[1], yv[2], yv[3]);
     else dst[o] = yv[0];
   }
-}
-
-// Philox4x32-10 (Salmon et al. 2011), counter = element-group index.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  float u2 = ((float)(b >> 8)) * (1.0f / 16777216.0f);
-  float rad = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  n0 = rad * c;
-  n1 = rad * s;
 }
 
 template <bool RICIAN>
@@ -253,14 +189,6 @@ noise_philox_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
     if (vec) *(float4*)(dst + o) = make_float4(yv[0], yv[1], yv[2], yv[3]);
     else for (int v = 0; v < cnt; ++v) dst[o + v] = yv[v];
   }
-}
-
-__device__ __forceinline__ float signed_pow(float x, float gam) {
-  // sign(x) * |x|^gamma ; x == 0 -> 0 ; gamma == 1 -> x exactly (identity rows)
-  if (gam == 1.0f) return x;
-  float ax = fabsf(x);
-  float p = powf(ax, gam);
-  return x > 0.0f ? p : (x < 0.0f ? -p : __fmul_rn(0.0f, p));
 }
 
 template <int V>
@@ -330,44 +258,6 @@ extern "C" int tio_bias_field(const float* src, float* dst, int B, int C, int I,
     bias_kernel<1><<<grid, block, smem, st>>>(src, dst, C, I, J, K, coarse, si, sj, sk,
                                               scale(si, I), scale(sj, J), scale(sk, K), identity,
                                               divide);
-  }
-  TIO_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int tio_blur(const float* src, float* dst, float* scratch, int B, int C, int I, int J,
-                        int K, const float* taps, const int32_t* radius, int R, int axes_mask,
-                        const uint8_t* identity, void* stream) {
-  (void)identity;  // rows with all radii 0 are copied exactly by every pass
-  TIO_CHECK_ARG(src && dst && taps && radius, "tio_blur: null pointer");
-  TIO_CHECK_ARG(src != dst, "tio_blur: src and dst must not alias");
-  TIO_CHECK_ARG(B > 0 && C > 0 && I > 0 && J > 0 && K > 0 && R >= 0, "tio_blur: bad shape");
-  const int n_axes = ((axes_mask >> 0) & 1) + ((axes_mask >> 1) & 1) + ((axes_mask >> 2) & 1);
-  TIO_CHECK_ARG(n_axes < 2 || scratch, "tio_blur: scratch required for >= 2 active axes");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t bytes = (int64_t)B * C * I * J * K * 4;
-  if (n_axes == 0) {
-    TIO_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
-    return 0;
-  }
-  // ping-pong so that the last active pass lands in dst
-  const float* cur = src;
-  int remaining = n_axes;
-  dim3 block(64, 4);
-  TIO_CHECK_ARG((int64_t)B * C <= 65535 && (int64_t)I * ((J + 3) / 4) <= 65535,
-                "tio_blur: grid too large");
-  dim3 grid((K + 63) / 64, I * ((J + 3) / 4), B * C);
-  for (int axis = 0; axis < 3; ++axis) {
-    if (!((axes_mask >> axis) & 1)) continue;
-    float* out = (remaining % 2 == 1) ? dst : scratch;
-    if (axis == 0)
-      blur_axis_kernel<0><<<grid, block, 0, st>>>(cur, out, C, I, J, K, taps, radius, B, R);
-    else if (axis == 1)
-      blur_axis_kernel<1><<<grid, block, 0, st>>>(cur, out, C, I, J, K, taps, radius, B, R);
-    else
-      blur_axis_kernel<2><<<grid, block, 0, st>>>(cur, out, C, I, J, K, taps, radius, B, R);
-    cur = out;
-    --remaining;
   }
   TIO_CHECK_LAUNCH();
   return 0;

@@ -164,14 +164,13 @@ def blur(src: Tensor, taps: Tensor, radius: Tensor, big_r: int, axes_mask: int,
     src = src.contiguous()
     b, c, i, j, k = src.shape
     dst = torch.empty_like(src)
-    n_axes = bin(axes_mask & 7).count("1")
-    scratch = torch.empty_like(src) if n_axes >= 2 else None
+    scratch = torch.empty_like(src) if (axes_mask & 6) else None
     with torch.cuda.device(src.device):
         _native.call(
             "tio_blur", _ptr(src), _ptr(dst), _ptr(scratch), b, c, i, j, k, _ptr(taps),
             _ptr(radius), int(big_r), int(axes_mask), _ptr(identity), _stream(src),
         )
-    _count(max(n_axes, 1))
+    _count(2 if (axes_mask & 6) else 1)
     return dst
 
 
@@ -216,4 +215,39 @@ def gamma(src: Tensor, gam: Tensor) -> Tensor:
             _stream(src),
         )
     _count(1)
+    return dst
+
+
+def intensity_fused(
+    src: Tensor, *, coarse: Tensor | None = None, bias_identity: Tensor | None = None,
+    bias_divide: bool = False, taps: Tensor | None = None, radius: Tensor | None = None,
+    big_r: int = 0, axes_mask: int = 0, mean: Tensor | None = None, std: Tensor | None = None,
+    keep: Tensor | None = None, z: Tensor | None = None, z2: Tensor | None = None,
+    philox_seed: int = 0, noise_mode: int = 0, rician: bool = False,
+    gamma: Tensor | None = None,
+) -> Tensor:
+    """Fused bias -> blur -> noise -> gamma (two HBM passes); any stage optional.
+
+    Compose-level fusion of consecutive intensity transforms; equal to running
+    `bias_field`, `blur`, `noise`, `gamma` in sequence up to fp32 summation order.
+    """
+    _require_cuda(src, "intensity_fused")
+    src = src.contiguous()
+    b, c, i, j, k = src.shape
+    dst = torch.empty_like(src)
+    jk = taps is not None and (axes_mask & 6)
+    scratch = torch.empty_like(src) if jk else None
+    si = sj = sk = 0
+    if coarse is not None:
+        si, sj, sk = coarse.shape[2:]
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_intensity_fused", _ptr(src), _ptr(dst), _ptr(scratch), b, c, i, j, k,
+            _ptr(coarse), si, sj, sk, _ptr(bias_identity), int(bool(bias_divide)),
+            _ptr(taps), _ptr(radius), int(big_r), int(axes_mask),
+            _ptr(mean), _ptr(std), _ptr(keep), _ptr(z), _ptr(z2),
+            int(philox_seed) & (2**64 - 1), int(noise_mode), int(bool(rician)),
+            _ptr(gamma), _stream(src),
+        )
+    _count(2 if jk else 1)
     return dst

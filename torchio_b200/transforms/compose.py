@@ -12,7 +12,10 @@ import copy as _copy
 from collections.abc import Mapping, Sequence
 from typing import Any
 
+import torch as _torch
+
 from .base import Transform, _Staging, _finish, wrap_input
+from . import intensity as _int
 
 
 class Compose(Transform):
@@ -37,9 +40,36 @@ class Compose(Transform):
     def _forward_batch(self, batch):
         # Children never copy (compose.py:88-92).  Unlike the reference we do
         # not mutate child.copy: Queue calls one Compose from several threads.
-        for transform in self.transforms:
-            batch = transform._forward_batch(batch)
+        index = 0
+        while index < len(self.transforms):
+            group = self._fusable_run(index) if self.fuse else []
+            if len(group) >= 2:
+                batch = _run_fused(group, batch)
+                index += len(group)
+            else:
+                batch = self.transforms[index]._forward_batch(batch)
+                index += 1
         return batch
+
+    #: Fuse runs of consecutive intensity transforms into one kernel pair.
+    fuse = True
+
+    def _fusable_run(self, start: int) -> list[Transform]:
+        """Longest run from ``start`` of BiasField < Blur < Noise < Gamma (each at
+        most once, in that order, same include/exclude): exactly the chains whose
+        per-voxel arithmetic the fused kernel reproduces."""
+        order = {_int.BiasField: 0, _int.Blur: 1, _int.Noise: 2, _int.Gamma: 3}
+        run: list[Transform] = []
+        last = -1
+        for transform in self.transforms[start:]:
+            rank = order.get(type(transform))
+            if rank is None or rank <= last:
+                break
+            if run and (transform.include != run[0].include or transform.exclude != run[0].exclude):
+                break
+            run.append(transform)
+            last = rank
+        return run
 
     def __len__(self) -> int:
         return len(self.transforms)
@@ -51,3 +81,32 @@ class Compose(Transform):
         cfg = super().to_hydra()
         cfg["transforms"] = [t.to_hydra() for t in self.transforms]
         return cfg
+
+
+def _run_fused(group: list[Transform], batch):
+    """Sample every transform of the run exactly as sequential application would
+    (gate draw, then make_params, in order — none of them reads voxel data),
+    then apply all non-gated stages with one fused launch pair per image."""
+    applied = []
+    builders = []
+    for transform in group:
+        # same draws as Transform._forward_batch
+        if not transform._per_instance_p_active(batch) and _torch.rand(1).item() >= transform.p:
+            continue
+        params = transform.make_params(batch)
+        applied.append((transform, params))
+        if isinstance(transform, _int.BiasField):
+            builders.append(lambda ib, index, p=params: _int._bias_stage(
+                ib.data.shape, ib.affines, p["std"], p["seed"], p["scale"], divide=False))
+        elif isinstance(transform, _int.Blur):
+            builders.append(lambda ib, index, p=params: _int._blur_stage(ib, p))
+        elif isinstance(transform, _int.Noise):
+            builders.append(_int._noise_stage_factory(params))
+        else:
+            builders.append(lambda ib, index, p=params: {
+                "gamma": _int.tables.gamma_values(p["log_gamma"], ib.data.shape[0])})
+    if applied:
+        _int.run_stages(group[0]._get_images(batch), builders)
+        for transform, params in applied:
+            transform._record(batch, params)
+    return batch

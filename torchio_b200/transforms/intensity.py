@@ -70,25 +70,29 @@ class BiasField(IntensityTransform):
                                  copy=False)
 
 
-def _apply_bias(transform, batch, std, seed, scale, *, divide: bool) -> None:
+def _bias_stage(data_shape, affines, std, seed, scale, *, divide: bool):
+    """Host tables of the bias stage, or None when the transform is a no-op
+    (bias_field.py:105-107,223-225)."""
     per_element = isinstance(std, list)
-    if not per_element and std == 0:
-        return
-    if per_element and all(s == 0 for s in std):
-        return
-    for ib in transform._get_images(batch).values():
-        data = ib.data
-        b = data.shape[0]
-        if per_element and len(std) != b:
-            raise RuntimeError(
-                f"Per-instance parameters were recorded for {len(std)} elements"
-                f" but the batch has {b}"
-            )
-        coarse = tables.coarse_bias_fields(data.shape, std, seed, scale)
-        identity = np.asarray([s == 0 for s in std], dtype=np.uint8) if per_element else None
-        coarse_d, identity_d = ops.upload(data.device, coarse, identity)
-        out = ops.bias_field(_as_f32(data), coarse_d, identity_d, divide=divide)
-        ib.data = out if per_element is False or out.dtype == data.dtype else out.to(data.dtype)
+    if (not per_element and std == 0) or (per_element and all(s == 0 for s in std)):
+        return None
+    b = data_shape[0]
+    if per_element and len(std) != b:
+        raise RuntimeError(
+            f"Per-instance parameters were recorded for {len(std)} elements"
+            f" but the batch has {b}"
+        )
+    return {
+        "coarse": tables.coarse_bias_fields(data_shape, std, seed, scale),
+        "bias_identity": np.asarray([s == 0 for s in std], dtype=np.uint8) if per_element else None,
+        "bias_divide": divide,
+    }
+
+
+def _apply_bias(transform, batch, std, seed, scale, *, divide: bool) -> None:
+    run_stages(transform._get_images(batch),
+               [lambda ib, index: _bias_stage(ib.data.shape, ib.affines, std, seed, scale,
+                                              divide=divide)])
 
 
 class _BiasFieldInverse(IntensityTransform):
@@ -131,23 +135,24 @@ class Blur(IntensityTransform):
         return params
 
     def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
-        per_instance = self._is_per_instance_params(params)
-        for ib in self._get_images(batch).values():
-            data = ib.data
-            if per_instance:
-                mm = np.asarray(params["std"], dtype=np.float64)
-                sp = np.asarray([a.spacing for a in ib.affines], dtype=np.float64)
-                vox = np.divide(mm, sp, out=np.zeros_like(mm), where=sp > 0)
-            else:
-                sp = np.asarray(ib.affines[0].spacing, dtype=np.float64)
-                vox = [s / q if q > 0 else 0.0 for s, q in zip(params["std"], sp, strict=True)]
-            t = tables.blur_tables(vox, data.shape[0])
-            if t is None:  # all sigma <= 0: the input tensor itself (blur.py:143-144)
-                continue
-            taps, radius, identity = ops.upload(data.device, t.taps, t.radius, t.identity)
-            out = ops.blur(_as_f32(data), taps, radius, t.big_r, t.axes_mask, identity)
-            ib.data = out if out.dtype == data.dtype else out.to(data.dtype)
+        run_stages(self._get_images(batch), [lambda ib, index: _blur_stage(ib, params)])
         return batch
+
+
+def _blur_stage(ib, params):
+    """Host tables of the blur stage, or None when every sigma <= 0 (the
+    reference then returns the input tensor itself, blur.py:143-144)."""
+    if "_batched_keys" in params:
+        mm = np.asarray(params["std"], dtype=np.float64)
+        sp = np.asarray([a.spacing for a in ib.affines], dtype=np.float64)
+        vox = np.divide(mm, sp, out=np.zeros_like(mm), where=sp > 0)
+    else:
+        sp = np.asarray(ib.affines[0].spacing, dtype=np.float64)
+        vox = [s / q if q > 0 else 0.0 for s, q in zip(params["std"], sp, strict=True)]
+    t = tables.blur_tables(vox, ib.data.shape[0])
+    if t is None:
+        return None
+    return {"taps": t.taps, "radius": t.radius, "big_r": t.big_r, "axes_mask": t.axes_mask}
 
 
 # ---- Noise (intensity/noise.py:18-178) -----------------------------------------
@@ -193,35 +198,45 @@ class Noise(IntensityTransform):
         return params
 
     def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
-        rician = params.get("rician", False)
-        keep = params.get("_keep")
-        mode = _noise_mode()
-        generator = torch.Generator(device="cpu")
-        generator.manual_seed(params["seed"])
-        for index, ib in enumerate(self._get_images(batch).values()):
-            data = ib.data
-            b = data.shape[0]
-            mean = tables.per_element_vector(params["mean"], b)
-            std = tables.per_element_vector(params["std"], b)
-            keep_np = None if keep is None else np.asarray(keep, dtype=np.uint8)
-            mean_d, std_d, keep_d = ops.upload(data.device, mean, std, keep_np)
-            x = _as_f32(data)
-            if mode == "philox":
-                seed = (int(params["seed"]) << 8) | (index & 0xFF)
-                ib.data = ops.noise_philox(x, mean_d, std_d, keep_d, seed, rician)
-                continue
-            # one CPU generator, consumed in flat (B,C,I,J,K) order, continuing
-            # across images and across the second Rician draw (noise.py:166-178)
-            pin = torch.cuda.is_available()
-            z = torch.empty(data.shape, dtype=torch.float32, pin_memory=pin)
-            torch.randn(data.shape, generator=generator, out=z)
-            z2 = None
-            if rician:
-                z2 = torch.empty(data.shape, dtype=torch.float32, pin_memory=pin)
-                torch.randn(data.shape, generator=generator, out=z2)
-                z2 = z2.to(data.device, non_blocking=True)
-            ib.data = ops.noise(x, mean_d, std_d, keep_d, z.to(data.device, non_blocking=True), z2)
+        run_stages(self._get_images(batch), [_noise_stage_factory(params)])
         return batch
+
+
+def _noise_stage_factory(params):
+    """One CPU generator per transform application, consumed in flat
+    (B,C,I,J,K) order and continuing across images and across the second
+    Rician draw (noise.py:109-118,166-178)."""
+    mode = _noise_mode()
+    generator = torch.Generator(device="cpu")
+    generator.manual_seed(params["seed"])
+    rician = bool(params.get("rician", False))
+    keep = params.get("_keep")
+
+    def stage(ib, index):
+        shape = ib.data.shape
+        b = shape[0]
+        out = {
+            "mean": tables.per_element_vector(params["mean"], b),
+            "std": tables.per_element_vector(params["std"], b),
+            "keep": None if keep is None else np.asarray(keep, dtype=np.uint8),
+            "rician": rician,
+        }
+        if mode == "philox":
+            out["noise_mode"] = 2
+            out["philox_seed"] = (int(params["seed"]) << 8) | (index & 0xFF)
+            return out
+        pin = torch.cuda.is_available()
+        out["noise_mode"] = 1
+        z = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+        torch.randn(shape, generator=generator, out=z)
+        out["z_host"] = z
+        if rician:
+            z2 = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+            torch.randn(shape, generator=generator, out=z2)
+            out["z2_host"] = z2
+        return out
+
+    return stage
 
 
 # ---- Gamma (intensity/gamma.py:17-149) ------------------------------------------
@@ -262,11 +277,8 @@ class Gamma(IntensityTransform):
 
 
 def _apply_gamma(transform, batch, log_gamma) -> None:
-    for ib in transform._get_images(batch).values():
-        data = ib.data
-        gam = tables.gamma_values(log_gamma, data.shape[0])
-        (gam_d,) = ops.upload(data.device, gam)
-        ib.data = ops.gamma(_as_f32(data), gam_d)
+    run_stages(transform._get_images(batch),
+               [lambda ib, index: {"gamma": tables.gamma_values(log_gamma, ib.data.shape[0])}])
 
 
 class _GammaInverse(IntensityTransform):
@@ -278,3 +290,42 @@ class _GammaInverse(IntensityTransform):
         lg = self._log_gamma
         _apply_gamma(self, batch, [-v for v in lg] if isinstance(lg, list) else -lg)
         return batch
+
+
+# ---- shared runner: 1..4 stages -> one fused launch pair per image ---------------
+
+_TABLE_KEYS = ("coarse", "bias_identity", "taps", "radius", "mean", "std", "keep", "gamma")
+
+
+def run_stages(images, stage_builders) -> None:
+    """Build the host tables of every stage for every selected image, upload
+    them with one staging copy per image and run `ops.intensity_fused`.
+
+    ``stage_builders``: callables ``(images_batch, image_index) -> dict | None``
+    in pipeline order bias < blur < noise < gamma (None = that stage is a no-op
+    for this image).  Used by the individual transforms (one stage) and by
+    `Compose` when it fuses consecutive intensity transforms."""
+    for index, ib in enumerate(images.values()):
+        kwargs: dict[str, Any] = {}
+        for build in stage_builders:
+            stage = build(ib, index)
+            if stage:
+                kwargs.update(stage)
+        if not kwargs:
+            continue
+        data = ib.data
+        device = data.device
+        uploaded = ops.upload(device, *[kwargs.get(k) for k in _TABLE_KEYS])
+        for key, value in zip(_TABLE_KEYS, uploaded, strict=True):
+            if key in kwargs:
+                kwargs[key] = value
+        z_host, z2_host = kwargs.pop("z_host", None), kwargs.pop("z2_host", None)
+        if z_host is not None:
+            kwargs["z"] = z_host.to(device, non_blocking=True)
+        if z2_host is not None:
+            kwargs["z2"] = z2_host.to(device, non_blocking=True)
+        out = ops.intensity_fused(_as_f32(data), **kwargs)
+        # bias/blur return the input dtype (bias_field.py:245, blur.py:204,248);
+        # noise/gamma follow torch type promotion against their fp32 operands
+        promotes = ("gamma" in kwargs or "mean" in kwargs) and data.dtype != torch.float64
+        ib.data = out if promotes or out.dtype == data.dtype else out.to(data.dtype)
