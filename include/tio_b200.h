@@ -73,6 +73,13 @@ int tio_abi_version(void);
  *              (the reference skips it only for a python-float 0.0 fill,
  *              spatial.py:2072-2076).  The mask is always the TRILINEAR
  *              in-bounds weight sum, even for nearest data (:1722-1727).
+ *   box_hint   host int selecting the kernel: < 0 = general gather kernel only
+ *              (exact mul+add tap sum); 0 = TMA tile path with the default
+ *              24^3 input box; 20 / 24 / 32 = TMA tile path with that box edge
+ *              (callers that know the matrices pick the smallest box covering
+ *              the pre-image of a 16^3 output tile).  The tile path applies to
+ *              fp32 + TIO_LINEAR with K % 4 == 0; anything else, and any tile
+ *              whose pre-image does not fit, uses the general kernel.
  * src and dst must not alias.
  */
 int tio_resample(const void* src, void* dst, int dtype,
@@ -81,7 +88,7 @@ int tio_resample(const void* src, void* dst, int dtype,
                  const float* mat, const float* cp, const uint8_t* flags,
                  int ni, int nj, int nk,
                  const float* spacing_in, const float* spacing_out,
-                 int affine_first, int mode, const float* fill,
+                 int affine_first, int mode, const float* fill, int box_hint,
                  void* stream);
 
 /*

@@ -39,8 +39,10 @@ def test_cuda_matches_reference_golden(name):
         else:
             assert r["max_abs_over_range"] <= TOL_RANGE, (n, r)
         ro = report(got, oracle[n]["data"])
-        if only_spatial:  # same arithmetic, same order: bit-exact vs the C oracle
-            assert ro["n_mismatch"] == 0, (n, ro)
+        if only_spatial and images[n]["kind"] == "label":
+            assert ro["n_mismatch"] == 0, (n, ro)  # same coordinates, same rounding
+        elif only_spatial:  # same coordinates; taps blended with FMA lerps (<= 1 ulp)
+            assert ro["max_abs_over_range"] <= 3e-7, (n, ro)
         else:
             assert ro["max_abs_over_range"] <= 2e-6, (n, ro)
         for b, a in enumerate(out.images[n].affines):

@@ -32,7 +32,7 @@ def _random_matrix(rng, shape, big=False):
     return m.astype(np.float32)[:3].reshape(12)
 
 
-def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill):
+def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill, box_hint=-1):
     from torchio_b200 import ops
 
     c_port = _orc()
@@ -46,7 +46,7 @@ def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill):
     got = ops.resample(
         data.to(dev), mat_t.to(dev), None if cp_t is None else cp_t.to(dev),
         None if fl_t is None else fl_t.to(dev), sp_in, sp_out, affine_first=affine_first,
-        mode=mode, fill=None if fill_t is None else fill_t.to(dev),
+        mode=mode, fill=None if fill_t is None else fill_t.to(dev), box_hint=box_hint,
     ).cpu()
     want = torch.empty_like(data)
     ni, nj, nk = (0, 0, 0) if cp is None else cp.shape[1:4]
@@ -61,7 +61,7 @@ def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill):
     return got, want
 
 
-SHAPES = [(33, 29, 70), (16, 16, 1), (7, 5, 3), (64, 48, 40)]
+SHAPES = [(33, 29, 70), (16, 16, 1), (7, 5, 3), (64, 48, 40), (40, 36, 64), (18, 50, 4)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -84,6 +84,17 @@ def test_resample_bit_exact_vs_c_oracle(shape, mode, elastic):
             got, want = _run_both(data, mat, cp, flags, (0.8, 1.1, 2.0), (0.8, 1.1, 2.0),
                                   affine_first, mode, fill)
             assert torch.equal(got, want), int((got != want).sum())
+            if mode == 1:
+                # TMA tile path: same coordinates and fill decisions, FMA tap blending
+                for hint in (0, 20, 32):
+                    fast, _ = _run_both(data, mat, cp, flags, (0.8, 1.1, 2.0), (0.8, 1.1, 2.0),
+                                        affine_first, mode, fill, box_hint=hint)
+                    assert float((fast - want).abs().max()) <= 1e-6
+                    if fill is not None:
+                        for ch in range(c):
+                            filled_fast = fast[:, ch] == float(fill[ch])
+                            filled_want = want[:, ch] == float(fill[ch])
+                            assert torch.equal(filled_fast, filled_want)
 
 
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64])

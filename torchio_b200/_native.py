@@ -19,7 +19,7 @@ _SIGNATURES = {
     "tio_abi_version": [],
     "tio_resample": [c_void_p, c_void_p, c_int] + [c_int] * 8
     + [c_void_p, c_void_p, c_void_p] + [c_int] * 3
-    + [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    + [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "tio_min_sample0": [c_void_p, c_int, c_int64, c_void_p, c_void_p],
     "tio_bias_field": [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 3
     + [c_void_p, c_int, c_void_p],

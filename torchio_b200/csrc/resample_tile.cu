@@ -1,0 +1,538 @@
+// resample_tile.cu — K1 fast path: fp32, trilinear, TMA-staged input tiles.
+//
+// One CTA produces a 16 x 16 x 16 output tile.  Warp 0 bounds the tile's
+// pre-image in input voxel space (affine corners by interval arithmetic,
+// elastic displacement by evaluating the piecewise-trilinear field at the
+// tile corners and control-cell crossings, where its extrema lie), and one
+// thread issues a single 4-D TMA box load (cp.async.bulk.tensor, zero fill
+// outside the volume = grid_sample's padding_mode="zeros").  256 threads then
+// walk the 16 planes of their (j,k) column reading the 8 taps from shared
+// memory.  Tiles whose pre-image does not fit the box fall back to the
+// general global-memory column (same results).
+//
+// Coordinates reproduce the reference's CPU rounding sequence exactly
+// (oracle/c/tio_oracle.c); the divide by (size-1)/2 uses the reciprocal +
+// two-FMA correction, admitted per divisor only after an exhaustive on-device
+// check against __fdiv_rn over every float (see verify_fastdiv).  Tap blending
+// uses FMA lerps (<= 1 ulp from the reference's mul+add chain).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+
+#include "resample_common.cuh"
+
+namespace tio {
+
+constexpr int XT = 16;  // output tile edge
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: floor() via round-down add
+constexpr int kMagicBits = 0x4B400000;
+
+struct TileArgs {
+  float hd[3];   // max(size-1,1)/2      (divisor of the normalise step, exact)
+  float rcp[3];  // rn(1/hd)
+  float hs[3];   // (size-1)/2           (ATen un-normalise multiplier, exact)
+  int sp_in_one, sp_out_one;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <bool FASTDIV>
+__device__ __forceinline__ float norm_div(float x, float hd, float rcp) {
+  if (FASTDIV) {
+    const float q0 = __fmul_rn(x, rcp);
+    const float e = __fmaf_rn(-q0, hd, x);
+    return __fmaf_rn(e, rcp, q0);
+  }
+  return __fdiv_rn(x, hd);
+}
+
+// trilinear displacement (3 components) at one output position, exact ATen order
+__device__ __forceinline__ void disp_at(const float* g, const ResampleArgs& a, int oi, int oj,
+                                        int ok, float d[3]) {
+  const LerpAxis li = lerp_axis(a.sc_i, a.ni, oi);
+  const LerpAxis lj = lerp_axis(a.sc_j, a.nj, oj);
+  const LerpAxis lk = lerp_axis(a.sc_k, a.nk, ok);
+  const int plane = a.nj * a.nk * 3;
+  const float* p0 = g + li.i0 * plane;
+  const float* p1 = g + li.i1 * plane;
+  const int o00 = (lj.i0 * a.nk + lk.i0) * 3, o01 = (lj.i0 * a.nk + lk.i1) * 3;
+  const int o10 = (lj.i1 * a.nk + lk.i0) * 3, o11 = (lj.i1 * a.nk + lk.i1) * 3;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
+    float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
+    float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
+    float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
+    d[ax] = lerp2(li.l0, lerp2(lj.l0, a00, lj.l1, a01), li.l1, lerp2(lj.l0, b00, lj.l1, b01));
+  }
+}
+
+// Sample positions along one axis where a piecewise-linear (in `scale*o`)
+// function over integers o in [lo, hi] can attain its extrema: both ends and
+// the integers adjacent to every breakpoint.  Returns count (<= 8) or -1
+// (pts must hold 12 entries).
+__device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts) {
+  int n = 0;
+  pts[n++] = lo;
+  if (hi > lo) {
+    const float rlo = scale * (float)lo, rhi = scale * (float)hi;
+    const int c_first = (int)floorf(rlo) + 1, c_last = (int)ceilf(rhi) - 1;
+    for (int c = c_first; c <= c_last; ++c) {
+      if (n > 6) return -1;
+      const int o = (int)floorf((float)c / scale);
+      for (int t = o - 1; t <= o + 1; ++t)  // +-1 guards the fp32 division above
+        if (t > lo && t < hi && t > pts[n - 1]) pts[n++] = t;
+    }
+    pts[n++] = hi;
+    if (n > 8) return -1;
+  }
+  return n;
+}
+
+template <int BOX, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
+__global__ void __launch_bounds__(256)
+resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArgs a,
+                     const TileArgs ta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [box: BOX^3 floats | cp: ncp floats | ctl]
+  float* box = (float*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  float* cps = box + BOX * BOX * BOX;
+  const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
+  struct Ctl {
+    unsigned long long bar;
+    int ilo[3];
+    int fits, interior;
+    float dmin[3], dmax[3];
+  };
+  Ctl* ctl = (Ctl*)(((uintptr_t)(cps + ncp) + 15) & ~(uintptr_t)15);
+
+  const int tid = threadIdx.x;
+  const int tiles_i = (a.OI + XT - 1) / XT;
+  const int b = blockIdx.z / tiles_i;
+  const int i0 = (blockIdx.z % tiles_i) * XT;
+  const int j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
+  const int i1 = min(i0 + XT, a.OI) - 1, j1 = min(j0 + XT, a.OJ) - 1, k1 = min(k0 + XT, a.OK) - 1;
+  const int oj = j0 + (tid >> 4), ok = k0 + (tid & 15);
+  const bool active = (oj < a.OJ) && (ok < a.OK);
+  const int64_t n_in = (int64_t)a.I * a.J * a.K, n_out = (int64_t)a.OI * a.OJ * a.OK;
+  const uint8_t fl = a.flags ? a.flags[b] : 0;
+  const float* __restrict__ src = (const float*)a.src + (int64_t)b * a.C * n_in;
+  float* __restrict__ dst = (float*)a.dst + (int64_t)b * a.C * n_out;
+
+  if (fl & TIO_FLAG_PASSTHROUGH) {
+    if (active)
+      for (int c = 0; c < a.C; ++c)
+        for (int oi = i0; oi <= i1; ++oi) {
+          const int64_t o = ((int64_t)oi * a.OJ + oj) * a.OK + ok;
+          dst[c * n_out + o] = src[c * n_in + o];
+        }
+    return;
+  }
+  const bool elastic = HAS_CP && (fl & TIO_FLAG_ELASTIC);
+  if (elastic) {
+    const float* gsrc = a.cp + (int64_t)b * ncp;
+    for (int t = tid; t < ncp; t += 256) cps[t] = gsrc[t];
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ctl->bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  float m[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) m[t] = a.mat[b * 12 + t];
+  const int dims[3] = {a.I, a.J, a.K};
+
+  // ---------------- warp 0: bound the tile's pre-image ----------------
+  if (tid < 32) {
+    float dmn[3] = {0.f, 0.f, 0.f}, dmx[3] = {0.f, 0.f, 0.f};
+    bool ok_bounds = true;
+    if (elastic) {
+      int pi[12], pj[12], pk[12];
+      const int ni_ = axis_points(a.sc_i, i0, i1, pi);
+      const int nj_ = axis_points(a.sc_j, j0, j1, pj);
+      const int nk_ = axis_points(a.sc_k, k0, k1, pk);
+      if (ni_ < 0 || nj_ < 0 || nk_ < 0) {
+        ok_bounds = false;
+      } else {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) { dmn[ax] = 3.0e38f; dmx[ax] = -3.0e38f; }
+        const int total = ni_ * nj_ * nk_;
+        for (int t = tid; t < total; t += 32) {
+          const int tk = t % nk_, tj = (t / nk_) % nj_, ti = t / (nk_ * nj_);
+          float d[3];
+          disp_at(cps, a, pi[ti], pj[tj], pk[tk], d);
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) { dmn[ax] = fminf(dmn[ax], d[ax]); dmx[ax] = fmaxf(dmx[ax], d[ax]); }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            dmn[ax] = fminf(dmn[ax], __shfl_xor_sync(0xffffffffu, dmn[ax], s));
+            dmx[ax] = fmaxf(dmx[ax], __shfl_xor_sync(0xffffffffu, dmx[ax], s));
+          }
+      }
+    }
+    if (tid == 0) {
+      const float plo[3] = {(float)i0, (float)j0, (float)k0};
+      const float phi[3] = {(float)i1, (float)j1, (float)k1};
+      float elo[3], ehi[3], add_lo[3] = {0.f, 0.f, 0.f}, add_hi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) { elo[ax] = plo[ax]; ehi[ax] = phi[ax]; }
+      if (elastic) {
+        if (a.affine_first) {
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) { add_lo[ax] = dmn[ax] / a.sp_in[ax]; add_hi[ax] = dmx[ax] / a.sp_in[ax]; }
+        } else {
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) { elo[ax] += dmn[ax] / a.sp_out[ax]; ehi[ax] += dmx[ax] / a.sp_out[ax]; }
+        }
+      }
+      bool fits = ok_bounds, interior = true, outside = false;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        float qlo = m[4 * ax + 3], qhi = m[4 * ax + 3];
+#pragma unroll
+        for (int bx = 0; bx < 3; ++bx) {
+          const float v0 = m[4 * ax + bx] * elo[bx], v1 = m[4 * ax + bx] * ehi[bx];
+          qlo += fminf(v0, v1);
+          qhi += fmaxf(v0, v1);
+        }
+        qlo += add_lo[ax];
+        qhi += add_hi[ax];
+        const float margin = 0.02f + 1e-5f * fmaxf(fabsf(qlo), fabsf(qhi));
+        qlo -= margin;
+        qhi += margin;
+        if (dims[ax] == 1) { qlo = 0.0f; qhi = 0.0f; }  // (size-1) == 0 collapses the axis
+        if (!(fabsf(qlo) < 1.0e6f && fabsf(qhi) < 1.0e6f)) { fits = false; qlo = 0.f; qhi = 0.f; }
+        int lo = (int)floorf(qlo), hi = (int)floorf(qhi) + 1;
+        // every corner (floor(u), floor(u)+1) out of bounds on this axis => the
+        // whole tile is padding: value 0, mask 0
+        if (hi < 0 || lo > dims[ax] - 1) outside = true;
+        if (hi - lo + 1 > BOX) fits = false;
+        if (lo < 0 || hi > dims[ax] - 1) interior = false;
+        ctl->ilo[ax] = lo;
+      }
+      ctl->fits = (ok_bounds && outside) ? 2 : (fits ? 1 : 0);
+      ctl->interior = interior ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  const int fit_code = ctl->fits;
+  if (fit_code == 2) {  // pre-image entirely outside the volume
+    if (active)
+      for (int c = 0; c < a.C; ++c) {
+        const float v = HAS_FILL ? a.fill[c] : 0.0f;
+        for (int oi = i0; oi <= i1; ++oi)
+          dst[c * n_out + ((int64_t)oi * a.OJ + oj) * a.OK + ok] = v;
+      }
+    return;
+  }
+  if (fit_code == 0) {  // general global-memory path for this tile (CTA-uniform branch)
+    if (active)
+      general_column<float, TIO_LINEAR, HAS_CP, HAS_FILL>(a, b, elastic, elastic ? cps : nullptr, src,
+                                                          dst, n_in, n_out, i0, i1 + 1, oj, ok);
+    return;
+  }
+  const int ilo0 = ctl->ilo[0], ilo1 = ctl->ilo[1], ilo2 = ctl->ilo[2];
+  const bool tile_interior = ctl->interior != 0;
+
+  // per-thread displacement state (J/K levels cached across the I walk)
+  LerpAxis lj, lk;
+  int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+  if (elastic && active) {
+    lj = lerp_axis(a.sc_j, a.nj, oj);
+    lk = lerp_axis(a.sc_k, a.nk, ok);
+    o00 = (lj.i0 * a.nk + lk.i0) * 3; o01 = (lj.i0 * a.nk + lk.i1) * 3;
+    o10 = (lj.i1 * a.nk + lk.i0) * 3; o11 = (lj.i1 * a.nk + lk.i1) * 3;
+  }
+  const int plane = a.nj * a.nk * 3;
+  const float pj = (float)oj, pk = (float)ok;
+  constexpr int C1 = BOX * BOX, C2 = BOX;
+  const unsigned koff = (unsigned)(kMagicBits + ilo0) * C1 + (unsigned)(kMagicBits + ilo1) * C2 +
+                        (unsigned)(kMagicBits + ilo2);
+  const bool identity = !elastic ? false
+                                 : (m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f &&
+                                    m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[7] == 0.f &&
+                                    m[8] == 0.f && m[9] == 0.f && m[10] == 1.f && m[11] == 0.f);
+
+  for (int c = 0; c < a.C; ++c) {
+    if (tid == 0) {
+      const uint32_t bar = smem_u32(&ctl->bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                   "r"((uint32_t)(BOX * BOX * BOX * sizeof(float)))
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+          " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(box)),
+          "l"((unsigned long long)&tmap), "r"(ilo2), "r"(ilo1), "r"(ilo0), "r"(b * a.C + c), "r"(bar)
+          : "memory");
+    }
+    {  // wait for the box (phase parity = c & 1)
+      const uint32_t bar = smem_u32(&ctl->bar);
+      const uint32_t parity = (uint32_t)(c & 1);
+      uint32_t done;
+      do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      } while (!done);
+    }
+    if (active) {
+      int cur_i0 = -1, cur_i1 = -1;
+      float r_lo[3] = {0.f, 0.f, 0.f}, r_hi[3] = {0.f, 0.f, 0.f};
+      float* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
+      const int64_t ostride = (int64_t)a.OJ * a.OK;
+#pragma unroll 2
+      for (int oi = i0; oi <= i1; ++oi, out += ostride) {
+        const float pi = (float)oi;
+        float q0, q1, q2;
+        if (HAS_CP && elastic) {
+          const LerpAxis li = lerp_axis(a.sc_i, a.ni, oi);
+          if (li.i0 != cur_i0 || li.i1 != cur_i1) {
+            const float* p0 = cps + li.i0 * plane;
+            const float* p1 = cps + li.i1 * plane;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+              float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
+              float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
+              r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
+              float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
+              float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
+              r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
+            }
+            cur_i0 = li.i0; cur_i1 = li.i1;
+          }
+          float d0 = lerp2(li.l0, r_lo[0], li.l1, r_hi[0]);
+          float d1 = lerp2(li.l0, r_lo[1], li.l1, r_hi[1]);
+          float d2 = lerp2(li.l0, r_lo[2], li.l1, r_hi[2]);
+          if (a.affine_first) {
+            if (!ta.sp_in_one) { d0 = __fdiv_rn(d0, a.sp_in[0]); d1 = __fdiv_rn(d1, a.sp_in[1]); d2 = __fdiv_rn(d2, a.sp_in[2]); }
+            if (identity) {  // [p,1] @ I^T == p exactly
+              q0 = __fadd_rn(pi, d0); q1 = __fadd_rn(pj, d1); q2 = __fadd_rn(pk, d2);
+            } else {
+              q0 = __fadd_rn(affine_row(m + 0, pi, pj, pk), d0);
+              q1 = __fadd_rn(affine_row(m + 4, pi, pj, pk), d1);
+              q2 = __fadd_rn(affine_row(m + 8, pi, pj, pk), d2);
+            }
+          } else {
+            if (!ta.sp_out_one) { d0 = __fdiv_rn(d0, a.sp_out[0]); d1 = __fdiv_rn(d1, a.sp_out[1]); d2 = __fdiv_rn(d2, a.sp_out[2]); }
+            const float e0 = __fadd_rn(pi, d0), e1 = __fadd_rn(pj, d1), e2 = __fadd_rn(pk, d2);
+            q0 = affine_row(m + 0, e0, e1, e2);
+            q1 = affine_row(m + 4, e0, e1, e2);
+            q2 = affine_row(m + 8, e0, e1, e2);
+          }
+        } else {
+          q0 = affine_row(m + 0, pi, pj, pk);
+          q1 = affine_row(m + 4, pi, pj, pk);
+          q2 = affine_row(m + 8, pi, pj, pk);
+        }
+        // 2q/nm1 - 1  ->  ((g+1)/2)*(size-1), as rn(q/hd), -1, +1, *hs (all exact rescalings)
+        const float u0 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q0, ta.hd[0], ta.rcp[0]), 1.0f), 1.0f), ta.hs[0]);
+        const float u1 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q1, ta.hd[1], ta.rcp[1]), 1.0f), 1.0f), ta.hs[1]);
+        const float u2 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q2, ta.hd[2], ta.rcp[2]), 1.0f), 1.0f), ta.hs[2]);
+        // floor via round-down magic add: mantissa holds floor(u)
+        const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
+        const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2 = __fsub_rn(s2, kMagic);
+        const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2);
+        const int b0 = __float_as_int(s0), b1 = __float_as_int(s1), b2 = __float_as_int(s2);
+        const int off = (int)((unsigned)b0 * C1 + (unsigned)b1 * C2 + (unsigned)b2 - koff);
+        const float* p = box + off;
+        float v;
+        bool use_fill = false;
+        if (HAS_FILL && !tile_interior) {
+          const int c0 = b0 - kMagicBits, c1 = b1 - kMagicBits, c2 = b2 - kMagicBits;
+          const bool vox_interior = (c0 >= 0) & (c0 + 1 < a.I) & (c1 >= 0) & (c1 + 1 < a.J) &
+                                    (c2 >= 0) & (c2 + 1 < a.K);
+          if (!vox_interior) {  // exact ATen mask: ordered sum of in-bounds corner weights
+            const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
+                        lo2 = __fsub_rn(__fadd_rn(f2, 1.0f), u2);
+            const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
+            const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
+            const bool il = (c0 >= 0) & (c0 < a.I), ih = (c0 + 1 >= 0) & (c0 + 1 < a.I);
+            const bool jl = (c1 >= 0) & (c1 < a.J), jh = (c1 + 1 >= 0) & (c1 + 1 < a.J);
+            const bool kl = (c2 >= 0) & (c2 < a.K), kh = (c2 + 1 >= 0) & (c2 + 1 < a.K);
+            float msum = 0.0f;
+            if (il & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w00, lo2));
+            if (ih & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w10, lo2));
+            if (il & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w01, lo2));
+            if (ih & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w11, lo2));
+            if (il & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w00, hi2));
+            if (ih & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w10, hi2));
+            if (il & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w01, hi2));
+            if (ih & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w11, hi2));
+            use_fill = !(msum > 0.5f);
+          }
+        }
+        if (HAS_FILL && use_fill) {
+          v = a.fill[c];
+        } else {
+          // separable lerp K -> J -> I over the zero-padded box (<= 1 ulp from ATen's
+          // 8-term weighted sum; zero halo == skipping out-of-bounds corners)
+          const float v000 = p[0], v001 = p[1];
+          const float v010 = p[C2], v011 = p[C2 + 1];
+          const float v100 = p[C1], v101 = p[C1 + 1];
+          const float v110 = p[C1 + C2], v111 = p[C1 + C2 + 1];
+          const float a00 = __fmaf_rn(hi2, v001 - v000, v000);
+          const float a01 = __fmaf_rn(hi2, v011 - v010, v010);
+          const float a10 = __fmaf_rn(hi2, v101 - v100, v100);
+          const float a11 = __fmaf_rn(hi2, v111 - v110, v110);
+          const float bb0 = __fmaf_rn(hi1, a01 - a00, a00);
+          const float bb1 = __fmaf_rn(hi1, a11 - a10, a10);
+          v = __fmaf_rn(hi0, bb1 - bb0, bb0);
+        }
+        *out = v;
+      }
+    }
+    if (c + 1 < a.C) __syncthreads();  // box is reused by the next channel
+  }
+}
+
+// ---- exhaustive admission test of the reciprocal division --------------------
+__global__ void verify_fastdiv_kernel(float d, float r, unsigned long long* bad) {
+  const unsigned long long total = 1ull << 32;
+  unsigned long long local = 0;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned bits = (unsigned)t;
+    const unsigned ex = (bits >> 23) & 0xffu;
+    // quotients below 2^-25 all normalise to g = -1 exactly, so |x| < 2^-100 cannot
+    // change any coordinate; inf/nan never reach the fast path (box-fit test)
+    if (ex < 27u || ex > 190u) continue;
+    const float x = __uint_as_float(bits);
+    const float want = __fdiv_rn(x, d);
+    const float q0 = __fmul_rn(x, r);
+    const float q = __fmaf_rn(__fmaf_rn(-q0, d, x), r, q0);
+    local += (__float_as_uint(q) != __float_as_uint(want));
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+static std::mutex g_fd_mutex;
+static std::map<uint32_t, bool> g_fd_cache;
+
+// true iff rn(x*r) + 2-FMA correction == x/d for every float x (r = rn(1/d))
+static bool fastdiv_admitted(float d, cudaStream_t st) {
+  uint32_t key;
+  memcpy(&key, &d, 4);
+  {
+    std::lock_guard<std::mutex> lock(g_fd_mutex);
+    auto it = g_fd_cache.find(key);
+    if (it != g_fd_cache.end()) return it->second;
+  }
+  bool ok = false;
+  unsigned long long* bad = nullptr;
+  if (cudaMalloc(&bad, 8) == cudaSuccess) {
+    cudaMemsetAsync(bad, 0, 8, st);
+    verify_fastdiv_kernel<<<kNumSMs * 16, 256, 0, st>>>(d, (float)(1.0 / (double)d), bad);
+    unsigned long long host = 1;
+    if (cudaMemcpyAsync(&host, bad, 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess)
+      ok = (host == 0);
+    cudaFree(bad);
+  }
+  std::lock_guard<std::mutex> lock(g_fd_mutex);
+  g_fd_cache[key] = ok;
+  return ok;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+template <int BOX, bool HAS_CP, bool FASTDIV>
+static void launch_tile(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
+                        size_t smem, cudaStream_t st) {
+  if (a.fill) {
+    cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, true, FASTDIV>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resample_tile_kernel<BOX, HAS_CP, true, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta);
+  } else {
+    cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, false, FASTDIV>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resample_tile_kernel<BOX, HAS_CP, false, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta);
+  }
+}
+
+template <int BOX>
+static void launch_box(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
+                       size_t smem, bool fast, cudaStream_t st) {
+  if (a.cp) {
+    if (fast) launch_tile<BOX, true, true>(tm, a, ta, grid, smem, st);
+    else launch_tile<BOX, true, false>(tm, a, ta, grid, smem, st);
+  } else {
+    if (fast) launch_tile<BOX, false, true>(tm, a, ta, grid, smem, st);
+    else launch_tile<BOX, false, false>(tm, a, ta, grid, smem, st);
+  }
+}
+
+// Returns 0 when launched, 1 when the fast path does not apply (caller falls back),
+// >1 on error.
+int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
+  if ((a.K & 3) || ((uintptr_t)a.src & 15)) return 1;   // TMA strides must be 16-byte multiples
+  if ((int64_t)a.B * a.C > (1 << 30)) return 1;
+  const size_t ncp = a.cp ? (size_t)a.ni * a.nj * a.nk * 3 : 0;
+  if (ncp * 4 > 32 * 1024) return 1;
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return 1;
+  int box = box_hint <= 20 && box_hint > 0 ? 20 : (box_hint > 24 ? 32 : 24);
+  const int tiles_i = (a.OI + XT - 1) / XT;
+  if ((int64_t)a.B * tiles_i > 65535 || (a.OJ + XT - 1) / XT > 65535) return 1;
+
+  CUtensorMap tm;
+  const cuuint64_t gdim[4] = {(cuuint64_t)a.K, (cuuint64_t)a.J, (cuuint64_t)a.I, (cuuint64_t)a.B * a.C};
+  const cuuint64_t gstride[3] = {(cuuint64_t)a.K * 4, (cuuint64_t)a.J * a.K * 4,
+                                 (cuuint64_t)a.I * a.J * a.K * 4};
+  const cuuint32_t bdim[4] = {(cuuint32_t)box, (cuuint32_t)box, (cuuint32_t)box, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(a.src), gdim, gstride,
+                       bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return 1;
+
+  TileArgs ta;
+  const int dims[3] = {a.I, a.J, a.K};
+  bool fast = true;
+  for (int t = 0; t < 3; ++t) {
+    ta.hd[t] = a.nm1[t] * 0.5f;
+    ta.rcp[t] = (float)(1.0 / (double)ta.hd[t]);
+    ta.hs[t] = a.sm1[t] * 0.5f;
+    (void)dims;
+    fast = fast && fastdiv_admitted(ta.hd[t], st);
+  }
+  ta.sp_in_one = (a.sp_in[0] == 1.f && a.sp_in[1] == 1.f && a.sp_in[2] == 1.f);
+  ta.sp_out_one = (a.sp_out[0] == 1.f && a.sp_out[1] == 1.f && a.sp_out[2] == 1.f);
+
+  dim3 grid((a.OK + XT - 1) / XT, (a.OJ + XT - 1) / XT, (unsigned)(a.B * tiles_i));
+  const size_t smem = 128 + (size_t)box * box * box * 4 + ncp * 4 + 16 + 64;
+  if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, st);
+  else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, st);
+  else launch_box<32>(tm, a, ta, grid, smem, fast, st);
+  return 0;
+}
+
+}  // namespace tio

@@ -94,7 +94,7 @@ def upload(device: torch.device, *arrays):
 def resample(
     src: Tensor, mat: Tensor, cp: Tensor | None, flags: Tensor | None,
     spacing_in, spacing_out, *, affine_first: bool, mode: int,
-    fill: Tensor | None, out_shape=None,
+    fill: Tensor | None, out_shape=None, box_hint: int = 0,
 ) -> Tensor:
     """K1.  Replaces _build_sampling_grid + _sample_batch[_per_sample]
     (spatial/spatial.py:1504-1579,1651-1857).
@@ -120,7 +120,7 @@ def resample(
             "tio_resample", _ptr(src), _ptr(dst), DTYPE_CODES[src.dtype],
             b, c, i, j, k, oi, oj, ok, _ptr(mat), _ptr(cp), _ptr(flags), ni, nj, nk,
             sp_in.ctypes.data, sp_out.ctypes.data, int(bool(affine_first)), int(mode),
-            _ptr(fill), _stream(src),
+            _ptr(fill), int(box_hint), _stream(src),
         )
     _count(1)
     return dst

@@ -515,6 +515,7 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
         _check_folding(cp.shape[:3], disp, out_shape, sp_out)
     device = first.data.device
     mat_d, cp_d, flags_d = ops.upload(device, packed.mat, packed.cp, packed.flags)
+    box_hint = _box_hint(packed, a_in.spacing, a_out.spacing, out_shape)
     for name in names:
         ib = batch.images[name]
         is_label = issubclass(ib._image_class, LabelMap)
@@ -530,12 +531,39 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
             native, mat_d, cp_d, flags_d, a_in.spacing, a_out.spacing,
             affine_first=affine_first, mode=ops.NEAREST if interp == "nearest" else ops.LINEAR,
             fill=fill, out_shape=None if target_space is None else out_shape,
+            box_hint=box_hint,
         )
         ib.data = out if out.dtype == data.dtype else out.to(data.dtype)
         keep_original = set(packed.passthrough)
         ib.affines[:] = [
             ib.affines[i] if i in keep_original else a_out.clone() for i in range(b)
         ]
+
+
+def _box_hint(packed, sp_in, sp_out, out_shape) -> int:
+    """Edge (20/24/32) of the input box covering the pre-image of a 16^3 output
+    tile for every element: sum_b |M_ab| * 15 voxels + 2 taps, plus the largest
+    change an elastic field can make across the tile (adjacent control-point
+    deltas x control cells per voxel).  Tiles that still do not fit fall back to
+    the general path inside the kernel, so this only steers occupancy."""
+    m = np.abs(packed.mat.reshape(-1, 3, 4)[:, :, :3])
+    extent = (m.sum(axis=2) * 15.0).max(axis=0) + 2.0  # per input axis
+    if packed.cp is not None:
+        cp = packed.cp
+        spacing = np.minimum(np.asarray(sp_in, dtype=np.float64), np.asarray(sp_out))
+        variation = np.zeros(3)
+        for axis in range(3):
+            n_cp, n_out = cp.shape[1 + axis], out_shape[axis]
+            if n_cp > 1 and n_out > 1:
+                delta = np.abs(np.diff(cp, axis=1 + axis)).reshape(-1, 3).max(axis=0)
+                variation += delta * ((n_cp - 1) / (n_out - 1)) * 15.0
+        # all three partial derivatives peaking together is the rare case: budget a
+        # third of the worst case, outlier tiles take the in-kernel fallback
+        extent = extent + variation / spacing / 3.0
+    worst = float(np.max(extent))
+    if worst <= 20.0:
+        return 20
+    return 24 if worst <= 24.0 else 32
 
 
 class Affine(Spatial):
