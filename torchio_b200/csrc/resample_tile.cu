@@ -5,7 +5,10 @@
 // elastic displacement by evaluating the piecewise-trilinear field at the
 // tile corners and control-cell crossings, where its extrema lie), and one
 // thread issues a single 4-D TMA box load (cp.async.bulk.tensor, zero fill
-// outside the volume = grid_sample's padding_mode="zeros").  256 threads then
+// outside the volume = grid_sample's padding_mode="zeros").  The innermost box
+// coordinate must be a multiple of 16 bytes (probed: other values raise an
+// illegal-instruction fault), so the K origin is rounded down to a multiple
+// of 4 voxels and the box is BOX x BOX x (BOX+4).  256 threads then
 // walk the 16 planes of their (j,k) column reading the 8 taps from shared
 // memory.  Tiles whose pre-image does not fit the box fall back to the
 // general global-memory column (same results).
@@ -99,7 +102,8 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [box: BOX^3 floats | cp: ncp floats | ctl]
   float* box = (float*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  float* cps = box + BOX * BOX * BOX;
+  constexpr int BK = BOX + 4;  // inner (K) box extent: room for the 16-byte origin alignment
+  float* cps = box + BOX * BOX * BK;
   const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
   struct Ctl {
     unsigned long long bar;
@@ -115,7 +119,12 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const int i0 = (blockIdx.z % tiles_i) * XT;
   const int j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
   const int i1 = min(i0 + XT, a.OI) - 1, j1 = min(j0 + XT, a.OJ) - 1, k1 = min(k0 + XT, a.OK) - 1;
-  const int oj = j0 + (tid >> 4), ok = k0 + (tid & 15);
+  // lanes 0-15 / 16-31 of a warp take rows DJ apart: with row pitch BK the two
+  // half-warps then hit disjoint banks (DJ * BK == 16 mod 32) for axis-aligned reads
+  constexpr int DJ = (BOX == 20) ? 2 : 4;
+  const int warp = tid >> 5, half = (tid >> 4) & 1;
+  const int jrow = (warp % DJ) + (warp / DJ) * (2 * DJ) + half * DJ;
+  const int oj = j0 + jrow, ok = k0 + (tid & 15);
   const bool active = (oj < a.OJ) && (ok < a.OK);
   const int64_t n_in = (int64_t)a.I * a.J * a.K, n_out = (int64_t)a.OI * a.OJ * a.OK;
   const uint8_t fl = a.flags ? a.flags[b] : 0;
@@ -214,7 +223,8 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
         // every corner (floor(u), floor(u)+1) out of bounds on this axis => the
         // whole tile is padding: value 0, mask 0
         if (hi < 0 || lo > dims[ax] - 1) outside = true;
-        if (hi - lo + 1 > BOX) fits = false;
+        if (ax == 2) lo &= ~3;  // TMA: innermost coordinate must be 16-byte aligned
+        if (hi - lo + 1 > (ax == 2 ? BK : BOX)) fits = false;
         if (lo < 0 || hi > dims[ax] - 1) interior = false;
         ctl->ilo[ax] = lo;
       }
@@ -253,7 +263,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   }
   const int plane = a.nj * a.nk * 3;
   const float pj = (float)oj, pk = (float)ok;
-  constexpr int C1 = BOX * BOX, C2 = BOX;
+  constexpr int C1 = BOX * BK, C2 = BK;
   const unsigned koff = (unsigned)(kMagicBits + ilo0) * C1 + (unsigned)(kMagicBits + ilo1) * C2 +
                         (unsigned)(kMagicBits + ilo2);
   const bool identity = !elastic ? false
@@ -265,7 +275,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     if (tid == 0) {
       const uint32_t bar = smem_u32(&ctl->bar);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                   "r"((uint32_t)(BOX * BOX * BOX * sizeof(float)))
+                   "r"((uint32_t)(BOX * BOX * BK * sizeof(float)))
                    : "memory");
       asm volatile(
           "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -507,7 +517,7 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
   const cuuint64_t gdim[4] = {(cuuint64_t)a.K, (cuuint64_t)a.J, (cuuint64_t)a.I, (cuuint64_t)a.B * a.C};
   const cuuint64_t gstride[3] = {(cuuint64_t)a.K * 4, (cuuint64_t)a.J * a.K * 4,
                                  (cuuint64_t)a.I * a.J * a.K * 4};
-  const cuuint32_t bdim[4] = {(cuuint32_t)box, (cuuint32_t)box, (cuuint32_t)box, 1};
+  const cuuint32_t bdim[4] = {(cuuint32_t)box + 4, (cuuint32_t)box, (cuuint32_t)box, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(a.src), gdim, gstride,
                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -528,7 +538,7 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
   ta.sp_out_one = (a.sp_out[0] == 1.f && a.sp_out[1] == 1.f && a.sp_out[2] == 1.f);
 
   dim3 grid((a.OK + XT - 1) / XT, (a.OJ + XT - 1) / XT, (unsigned)(a.B * tiles_i));
-  const size_t smem = 128 + (size_t)box * box * box * 4 + ncp * 4 + 16 + 64;
+  const size_t smem = 128 + (size_t)box * box * (box + 4) * 4 + ncp * 4 + 16 + 64;
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, st);
   else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, st);
   else launch_box<32>(tm, a, ta, grid, smem, fast, st);
