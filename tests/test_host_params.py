@@ -38,3 +38,63 @@ def test_params_match_reference(name, fuse, monkeypatch):
     mine = _sample_only(transform, batch, monkeypatch, fuse)
     # JSON round trip == what the reference stores in history
     assert json.loads(json.dumps(mine)) == history
+
+
+SPECS = [
+    ("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10), "translation": (-3, 3)}),
+    ("Affine", {"scales": (0.8, 1.2), "isotropic": True, "degrees": (0, 0, -20, 20, 0, 0), "p": 0.6}),
+    ("ElasticDeformation", {}),
+    ("ElasticDeformation", {"max_displacement": (1.0, 6.0), "num_control_points": (5, 6, 7),
+                            "locked_borders": 1, "p": 0.5}),
+    ("Spatial", {"scales": (0.9, 1.1, 1.0, 1.0, 0.95, 1.05), "degrees": 5.0,
+                 "max_displacement": (0.0, 4.0, 0.0, 0.0, 2.0, 2.0), "affine_first": False}),
+]
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=[f"{n}-{i}" for i, (n, _) in enumerate(SPECS)])
+def test_vectorised_sampler_equals_per_element_loop(spec):
+    """The one-draw fast sampler consumes the RNG stream exactly like the
+    reference-shaped per-element loop (values, order, and what is left over)."""
+    import torchio_b200 as tio
+
+    name, kwargs = spec
+    images = {"t1": {"kind": "scalar", "data": torch.zeros(6, 1, 12, 10, 8),
+                     "affines": [__import__("numpy").eye(4)] * 6}}
+    results = []
+    for force_slow in (False, True):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = getattr(tio, name)(**kwargs)
+        if force_slow:
+            t._draw_plan = lambda: None
+        torch.manual_seed(77)
+        params = t.make_params(product_batch(images))
+        tail = torch.rand(3).tolist()  # the stream must be left in the same place
+        results.append((json.dumps(params, sort_keys=True), tail))
+    assert results[0] == results[1]
+
+
+def test_lazy_params_materialise_on_every_read_path():
+    import copy
+    import pickle
+
+    from torchio_b200.params import LazyParams
+
+    calls = []
+
+    def thunk():
+        calls.append(1)
+        return [[1.0, 2.0], None]
+
+    p = LazyParams({"a": 1})
+    p.set_lazy("m", thunk)
+    assert "m" in p and not calls and p["a"] == 1 and not calls
+    assert p["m"] == [[1.0, 2.0], None] and len(calls) == 1
+    for make in (lambda q: dict(q.items()), lambda q: json.loads(json.dumps(q)),
+                 lambda q: pickle.loads(pickle.dumps(q)), copy.deepcopy, lambda q: q.copy()):
+        q = LazyParams({"a": 1})
+        q.set_lazy("m", thunk)
+        assert make(q) == {"a": 1, "m": [[1.0, 2.0], None]}
+    q = LazyParams({"a": 1})
+    q.set_lazy("m", thunk)
+    assert q == {"a": 1, "m": [[1.0, 2.0], None]}

@@ -184,3 +184,95 @@ def to_nonneg_range(value) -> _ParameterRange:
     if pr._distribution is None and any(lo < 0 or hi < 0 for lo, hi in pr._ranges):
         raise ValueError(f"Value must be non-negative, got {value}")
     return pr
+
+
+class LazyParams(dict):
+    """``params`` dict whose bulky entries (per-element matrices, control grids)
+    are materialised to JSON-style nested lists on first access.
+
+    The reference serialises everything eagerly (``control_points.cpu().tolist()``
+    per element, transforms/spatial/spatial.py:2450-2468); for a batch of 32 that
+    is ~33k Python floats per transform and dominates a step once the kernels are
+    fast.  Reads (`[]`, ``get``, ``items``, ``values``, ``==``, ``repr``, pickling,
+    ``json.dumps``) force the entry, so observable content is identical."""
+
+    __slots__ = ("_lazy",)
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._lazy = {}
+
+    def set_lazy(self, key, thunk) -> None:
+        dict.__setitem__(self, key, None)
+        self._lazy[key] = thunk
+
+    def _force(self, key=None) -> None:
+        if not self._lazy:
+            return
+        for k in ([key] if key is not None else list(self._lazy)):
+            thunk = self._lazy.pop(k, None)
+            if thunk is not None:
+                dict.__setitem__(self, k, thunk())
+
+    def __getitem__(self, key):
+        if key in self._lazy:
+            self._force(key)
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        if key in self._lazy:
+            self._force(key)
+        return dict.get(self, key, default)
+
+    def __setitem__(self, key, value):
+        self._lazy.pop(key, None)
+        dict.__setitem__(self, key, value)
+
+    def items(self):
+        self._force()
+        return dict.items(self)
+
+    def values(self):
+        self._force()
+        return dict.values(self)
+
+    def copy(self):
+        self._force()
+        return dict(self)
+
+    def __eq__(self, other):
+        self._force()
+        if isinstance(other, LazyParams):
+            other._force()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._force()
+        return dict.__repr__(self)
+
+    def __reduce__(self):
+        self._force()
+        return (dict, (dict(self),))
+
+    def __deepcopy__(self, memo):
+        import copy as _copy
+
+        self._force()
+        return _copy.deepcopy(dict(self), memo)
+
+
+def uniform_from_unit(u, lo: float, hi: float):
+    """Map unit draws to ``uniform_(lo, hi)`` exactly as ATen's CPU kernel does:
+    fp32 ``fma(u, float(hi) - float(lo), float(lo))`` (probe-verified against
+    ``torch.empty(n).uniform_(lo, hi)``).  ``u``: float32 numpy array."""
+    import numpy as np
+
+    lo32 = np.float32(lo)
+    span = np.float32(np.float32(hi) - lo32)
+    # product of two fp32 values is exact in fp64; one rounding back to fp32
+    return (u.astype(np.float64) * np.float64(span) + np.float64(lo32)).astype(np.float32)

@@ -29,7 +29,7 @@ from torch.distributions import Distribution
 
 from .. import ops, tables
 from ..data import AffineMatrix, Image, ImagesBatch, LabelMap, SubjectsBatch
-from ..params import Choice, _ParameterRange
+from ..params import Choice, LazyParams, _ParameterRange, uniform_from_unit
 from .base import SpatialTransform
 
 _ORDERS = {
@@ -114,6 +114,12 @@ def _max_abs(cp: Tensor) -> tuple[float, float, float]:
 # ---- geometry (float64 host math, spatial.py:2269-2375) ------------------------
 
 
+def _close3(values, target: float) -> bool:
+    """np.allclose(values, target) for three finite scalars (rtol 1e-5, atol 1e-8)."""
+    tol = 1e-8 + 1e-5 * abs(target)
+    return all(abs(v - target) <= tol for v in values)
+
+
 def _rotation(degrees: np.ndarray) -> np.ndarray:
     rx, ry, rz = np.radians(degrees)
     cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
@@ -125,9 +131,9 @@ def _rotation(degrees: np.ndarray) -> np.ndarray:
 
 def build_forward_affine(scales, degrees, translation, center: str, shape, affine) -> np.ndarray:
     """World-space T = [R S | c - R S c + t], pivot at the image centre."""
-    scaling = np.asarray(scales, dtype=np.float64)
-    rotation = np.asarray(degrees, dtype=np.float64)
-    shift = np.asarray(translation, dtype=np.float64)
+    scaling = np.array(scales, dtype=np.float64)
+    rotation = np.array(degrees, dtype=np.float64)
+    shift = np.array(translation, dtype=np.float64)
     if shape[-1] == 1:  # 2-D input: suppress out-of-plane terms
         scaling[2] = 1.0
         rotation[0] = rotation[1] = 0.0
@@ -185,6 +191,9 @@ def _check_shared_space(images, shape, affine: AffineMatrix) -> None:
     for name, ib in images.items():
         if _shape_of(ib) != shape:
             raise RuntimeError(f'Image "{name}" has shape {_shape_of(ib)}, expected {shape}')
+        stacked = np.stack([a.numpy() for a in ib.affines])
+        if np.allclose(stacked, ref, rtol=1e-6, atol=1e-6):
+            continue
         for a in ib.affines:
             if not np.allclose(a.numpy(), ref, rtol=1e-6, atol=1e-6):
                 raise RuntimeError(
@@ -315,9 +324,7 @@ class Spatial(SpatialTransform):
         degrees = self.degrees.sample()
         translation = self.translation.sample()
         has_affine = not (
-            np.allclose(scales, (1.0, 1.0, 1.0))
-            and np.allclose(degrees, (0.0, 0.0, 0.0))
-            and np.allclose(translation, (0.0, 0.0, 0.0))
+            _close3(scales, 1.0) and _close3(degrees, 0.0) and _close3(translation, 0.0)
         )
         if self.control_points is not None:
             cp, max_disp = self.control_points.clone(), _max_abs(self.control_points)
@@ -331,6 +338,82 @@ class Spatial(SpatialTransform):
         if has_affine:
             forward = build_forward_affine(scales, degrees, translation, self.center, shape, affine)
         return forward, cp, max_disp
+
+    # -- vectorised per-instance sampling (same RNG stream, one draw) ----------
+
+    def _draw_plan(self):
+        """[(lo, hi) | constant] in the order `_sample_one` consumes the stream, or
+        None when a spec is not a plain number / (lo, hi) range."""
+        if self.control_points is not None:
+            return None
+        plan = []
+        groups = [self.scales._axes[:1] if self.isotropic else self.scales._axes,
+                  self.degrees._axes, self.translation._axes, self.max_displacement._axes]
+        for axes in groups:
+            for spec in axes:
+                if isinstance(spec, (int, float)):
+                    plan.append(float(spec))
+                elif isinstance(spec, tuple):
+                    plan.append(float(spec[0]) if spec[0] == spec[1] else (float(spec[0]), float(spec[1])))
+                else:
+                    return None
+        return plan
+
+    def _sample_batch_fast(self, n, keep, shape, affine):
+        """All kept elements from ONE `torch.rand` call that consumes exactly the
+        numbers the per-element loop would (uniform_ == fma(u, hi-lo, lo); a
+        block `torch.rand(m)` == m consecutive draws).  Returns None (RNG
+        untouched) when the fast plan does not apply."""
+        plan = self._draw_plan()
+        if plan is None:
+            return None
+        kept = [i for i in range(n) if keep is None or bool(keep[i])]
+        n_scalar = sum(isinstance(p, tuple) for p in plan)
+        disp_specs = plan[-3:]
+        elastic = not all(not isinstance(p, tuple) and p == 0.0 for p in disp_specs)
+        n_cp = int(np.prod(self.num_control_points)) * 3 if elastic else 0
+        per = n_scalar + n_cp
+        state = torch.get_rng_state() if (elastic and per) else None
+        u = torch.rand(len(kept) * per).numpy().reshape(len(kept), per) if per else None
+        cols, col = [], 0
+        for p in plan:
+            if isinstance(p, tuple):
+                cols.append(uniform_from_unit(u[:, col], *p).astype(np.float64))
+                col += 1
+            else:
+                cols.append(np.full(len(kept), p, dtype=np.float64))
+        values = np.stack(cols, axis=1) if cols else np.zeros((len(kept), 0))
+        ns = 1 if self.isotropic else 3
+        scales = np.repeat(values[:, :1], 3, axis=1) if self.isotropic else values[:, :3]
+        degrees, translation = values[:, ns:ns + 3], values[:, ns + 3:ns + 6]
+        max_disp = values[:, ns + 6:ns + 9]
+        if elastic and bool(np.any(np.all(max_disp == 0.0, axis=1))):
+            torch.set_rng_state(state)  # an all-zero draw skips the grid: replay the slow way
+            return None
+        forwards, cps, disps = [None] * n, [None] * n, [None] * n
+        tol1, tol0 = 1e-8 + 1e-5, 1e-8
+        has_affine = ~(np.all(np.abs(scales - 1.0) <= tol1, axis=1)
+                       & np.all(np.abs(degrees) <= tol0, axis=1)
+                       & np.all(np.abs(translation) <= tol0, axis=1))
+        fields = None
+        if elastic:
+            ni, nj, nk = self.num_control_points
+            fields = u[:, n_scalar:].reshape(len(kept), ni, nj, nk, 3).copy()
+            fields -= np.float32(0.5)
+            fields *= np.float32(2)
+            fields *= max_disp.astype(np.float32)[:, None, None, None, :]
+            for border in range(self.locked_borders):
+                fields[:, border] = 0; fields[:, -1 - border] = 0
+                fields[:, :, border] = 0; fields[:, :, -1 - border] = 0
+                fields[:, :, :, border] = 0; fields[:, :, :, -1 - border] = 0
+        for row, index in enumerate(kept):
+            if has_affine[row]:
+                forwards[index] = build_forward_affine(
+                    scales[row], degrees[row], translation[row], self.center, shape, affine)
+            if elastic:
+                cps[index] = fields[row]
+                disps[index] = [float(v) for v in max_disp[row]]
+        return forwards, cps, disps
 
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
         images = self._get_images(batch)
@@ -361,20 +444,27 @@ class Spatial(SpatialTransform):
             _packed.entry = (params, ([forward], [None if cp is None else cp.numpy()], False))
             return params
         keep = self._keep_mask(batch, n)
-        forwards, cps, disps = [], [], []
-        for index in range(n):
-            if keep is not None and not bool(keep[index]):
-                forwards.append(None); cps.append(None); disps.append(None)
-                continue
-            forward, cp, max_disp = self._sample_one(shape, affine)
-            forwards.append(forward)
-            cps.append(None if cp is None else cp.numpy())
-            disps.append(list(max_disp) if max_disp else None)
+        sampled = self._sample_batch_fast(n, keep, shape, affine)
+        if sampled is None:
+            forwards, cps, disps = [], [], []
+            for index in range(n):
+                if keep is not None and not bool(keep[index]):
+                    forwards.append(None); cps.append(None); disps.append(None)
+                    continue
+                forward, cp, max_disp = self._sample_one(shape, affine)
+                forwards.append(forward)
+                cps.append(None if cp is None else cp.numpy())
+                disps.append(list(max_disp) if max_disp else None)
+        else:
+            forwards, cps, disps = sampled
         if any(f is not None for f in forwards) or any(c is not None for c in cps):
             _check_shared_space(images, shape, affine)
+        params = LazyParams(params)
         params["target"] = _space_to_json(_resolve_target(self.target, batch, shape, affine))
-        params["affine_matrix"] = [None if f is None else f.tolist() for f in forwards]
-        params["control_points"] = [None if c is None else c.tolist() for c in cps]
+        params.set_lazy("affine_matrix",
+                        lambda: [None if f is None else f.tolist() for f in forwards])
+        params.set_lazy("control_points",
+                        lambda: [None if c is None else c.tolist() for c in cps])
         params["max_displacement"] = disps
         self._tag_batched(params, batch, n, keep,
                           ["affine_matrix", "control_points", "max_displacement"])
