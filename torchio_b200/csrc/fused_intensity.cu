@@ -4,16 +4,18 @@
 // transforms/intensity/{bias_field,blur,noise,gamma}.py; blur alone is
 // 3 x (F.pad replicate + F.conv3d), blur.py:171-252).
 //
-//   pass A  jk_kernel:   per (b,c) plane tile (32 x 64 outputs + halo) staged in
-//           shared memory; bias multiply at load; K-conv then J-conv; 8 B/voxel
-//           of HBM traffic, halo re-reads are L2 hits.
-//   pass B  march_kernel: thread <-> (j, 4 consecutive k), marching along I
-//           with a shared-memory ring of the last 2r+1 planes; I-conv, then
-//           noise (+Rician) and gamma as the store epilogue; 8 B/voxel
-//           (+4 B/voxel when normals are supplied, +4 for a second draw).
+//   pass 1  march_kernel: thread <-> (j, 4 consecutive k), marching along I
+//           with a shared-memory ring of the last 2r+1 planes; bias multiply at
+//           load (no halo, J/K lerp levels cached in registers), then I-conv;
+//           8 B/voxel.  Without J/K blur it also applies noise and gamma and is
+//           the only pass.
+//   pass 2  jk_kernel:   per (b,c) plane tile (32 x 64 outputs + halo) staged in
+//           shared memory; K-conv then J-conv; noise (+Rician) and gamma as the
+//           store epilogue; 8 B/voxel of HBM traffic (+4 when normals are
+//           supplied), halo re-reads are L2 hits.
 // Replicate padding == clamped addressing, so no padded copies exist.
 // Separable passes commute up to fp32 summation order (the reference runs
-// I, J, K; this runs K, J, I): differences are ~1e-7 relative.
+// I, J, K; this runs I, K, J): differences are ~1e-7 relative.
 #include "common.cuh"
 #include "intensity_common.cuh"
 
@@ -49,12 +51,12 @@ struct NoiseArgs {
 };
 
 // -------------------------------------------------------------------------
-// pass A
+// pass 2
 // -------------------------------------------------------------------------
-template <int RMAX, bool HAS_BIAS>
+template <int RMAX, bool HAS_EPI>
 __global__ void __launch_bounds__(256)
 jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int I, int J,
-          int K, BlurArgs bl, BiasArgs bi) {
+          int K, BlurArgs bl, NoiseArgs nz, const float* __restrict__ gamma) {
   constexpr int ROWS = A_TJ + 2 * RMAX;
   constexpr int COLS = A_TK + 2 * RMAX;
   constexpr int PITCH = (COLS + 3) / 4 * 4 + 4;  // 16-byte aligned rows
@@ -63,7 +65,6 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
   float* Bm = A + ROWS * PITCH;          // [ROWS][A_TK]    after the K pass
   float* tapk = Bm + ROWS * A_TK;        // [2*RMAX+1]
   float* tapj = tapk + (2 * RMAX + 1);   // [2*RMAX+1]
-  float* g = tapj + (2 * RMAX + 1);      // coarse bias grid (si*sj*sk)
 
   const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
   const int bc = blockIdx.z / tiles_i;
@@ -79,7 +80,9 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
   const int R = bl.taps ? bl.R : 0;
   const int rj = bl.taps ? bl.radius[1 * B + b] : 0;
   const int rk = bl.taps ? bl.radius[2 * B + b] : 0;
-  const bool bias_on = HAS_BIAS && !(bi.identity && bi.identity[b]);
+  const bool noise_on = HAS_EPI && nz.mode != 0 && (!nz.keep || nz.keep[b]);
+  const float mu = (HAS_EPI && nz.mode) ? nz.mean[b] : 0.0f, sd = (HAS_EPI && nz.mode) ? nz.std[b] : 0.0f;
+  const float gam = (HAS_EPI && gamma) ? gamma[b] : 1.0f;
 
   // taps shifted so that window offset s = 0..2r maps to tap (s - r); zero beyond
   if (tid < 2 * (2 * RMAX + 1)) {
@@ -90,11 +93,6 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
     if (bl.taps && rr > 0 && sft <= 2 * rr)
       v = bl.taps[((int64_t)(is_k ? 2 : 1) * B + b) * (2 * R + 1) + R - rr + sft];
     (is_k ? tapk : tapj)[sft] = v;
-  }
-  if (bias_on) {
-    const int ns = bi.si * bi.sj * bi.sk;
-    const float* gs = bi.coarse + (int64_t)bc * ns;
-    for (int t = tid; t < ns; t += 256) g[t] = gs[t];
   }
   __syncthreads();
 
@@ -107,28 +105,13 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
 
   for (int i = i_begin; i < i_end; ++i) {
     const float* xp = x + (int64_t)i * J * K;
-    LerpAxis li;
-    if (bias_on) li = lerp_axis(bi.sc_i, bi.si, i);
-    // ---- load (clamped = replicate padding), bias multiply at load ----
+    // ---- load (clamped = replicate padding) ----
     for (int r = ly; r < rows; r += 8) {
       const int jj = min(max(j0 - rj + r, 0), J - 1);
-      LerpAxis lj;
-      if (bias_on) lj = lerp_axis(bi.sc_j, bi.sj, jj);
+      const float* xr = xp + (int64_t)jj * K;
       for (int c = lx; c < cols; c += 32) {
         const int kk = min(max(k0 - rk + c, 0), K - 1);
-        float v = __ldg(xp + (int64_t)jj * K + kk);
-        if (bias_on) {
-          const LerpAxis lk = lerp_axis(bi.sc_k, bi.sk, kk);
-          const float* p0 = g + (li.i0 * bi.sj) * bi.sk;
-          const float* p1 = g + (li.i1 * bi.sj) * bi.sk;
-          float a0 = lerp2(lk.l0, p0[lj.i0 * bi.sk + lk.i0], lk.l1, p0[lj.i0 * bi.sk + lk.i1]);
-          float a1 = lerp2(lk.l0, p0[lj.i1 * bi.sk + lk.i0], lk.l1, p0[lj.i1 * bi.sk + lk.i1]);
-          float b0 = lerp2(lk.l0, p1[lj.i0 * bi.sk + lk.i0], lk.l1, p1[lj.i0 * bi.sk + lk.i1]);
-          float b1 = lerp2(lk.l0, p1[lj.i1 * bi.sk + lk.i0], lk.l1, p1[lj.i1 * bi.sk + lk.i1]);
-          float f = expf(lerp2(li.l0, lerp2(lj.l0, a0, lj.l1, a1), li.l1, lerp2(lj.l0, b0, lj.l1, b1)));
-          v = bi.divide ? __fdiv_rn(v, f) : __fmul_rn(v, f);
-        }
-        A[r * PITCH + c] = v;
+        A[r * PITCH + c] = __ldg(xr + kk);
       }
     }
     __syncthreads();
@@ -193,7 +176,44 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
         }
       }
       if (k < K) {
-        float* yp = y + (int64_t)i * J * K + k;
+        const int64_t plane_off = (int64_t)i * J * K + k;
+        if (HAS_EPI && noise_on) {
+          float z1[8], z2[8];
+          if (nz.mode == 1) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+              if (j0 + jy + o < J) {
+                const int64_t flat = (int64_t)bc * n + plane_off + (int64_t)(j0 + jy + o) * K;
+                z1[o] = __ldcs(nz.z + flat);
+                if (nz.rician) z2[o] = __ldcs(nz.z2 + flat);
+              }
+          } else {
+            const uint2 key = make_uint2((uint32_t)nz.philox_seed, (uint32_t)(nz.philox_seed >> 32));
+            const uint64_t gidx = (uint64_t)((int64_t)bc * n + plane_off + (int64_t)(j0 + jy) * K);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint4 rr = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)h, 0x6a6bu), key);
+              box_muller(rr.x, rr.y, z1[4 * h], z1[4 * h + 1]);
+              box_muller(rr.z, rr.w, z1[4 * h + 2], z1[4 * h + 3]);
+              if (nz.rician) {
+                uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)(2 + h), 0x6a6bu), key);
+                box_muller(r2.x, r2.y, z2[4 * h], z2[4 * h + 1]);
+                box_muller(r2.z, r2.w, z2[4 * h + 2], z2[4 * h + 3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const float n1 = __fadd_rn(mu, __fmul_rn(sd, z1[o]));
+            if (nz.rician) acc[o] = rician(acc[o], n1, __fadd_rn(mu, __fmul_rn(sd, z2[o])));
+            else acc[o] = __fadd_rn(acc[o], n1);
+          }
+        }
+        if (HAS_EPI && gamma) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] = signed_pow(acc[o], gam);
+        }
+        float* yp = y + plane_off;
 #pragma unroll
         for (int o = 0; o < 8; ++o)
           if (j0 + jy + o < J) yp[(int64_t)(j0 + jy + o) * K] = acc[o];
@@ -204,7 +224,7 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
 }
 
 // -------------------------------------------------------------------------
-// pass B
+// pass 1 (and the whole chain when no J/K blur is active)
 // -------------------------------------------------------------------------
 template <int V, bool HAS_BIAS>
 __global__ void __launch_bounds__(256)
@@ -387,20 +407,19 @@ static float up_scale(int n_in, int n_out) {
 
 template <int RMAX>
 static int launch_jk(const float* src, float* dst, int B, int C, int I, int J, int K,
-                     const BlurArgs& bl, const BiasArgs& bi, cudaStream_t st) {
+                     const BlurArgs& bl, const NoiseArgs& nz, const float* gamma, cudaStream_t st) {
   constexpr int ROWS = A_TJ + 2 * RMAX, COLS = A_TK + 2 * RMAX, PITCH = (COLS + 3) / 4 * 4 + 4;
-  const int ns = bi.coarse ? bi.si * bi.sj * bi.sk : 0;
-  const size_t smem = (size_t)(ROWS * PITCH + ROWS * A_TK + 2 * (2 * RMAX + 1) + ns) * sizeof(float);
+  const size_t smem = (size_t)(ROWS * PITCH + ROWS * A_TK + 2 * (2 * RMAX + 1)) * sizeof(float);
   const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
   dim3 grid((K + A_TK - 1) / A_TK, (J + A_TJ - 1) / A_TJ, B * C * tiles_i);
-  if (bi.coarse) {
+  if (nz.mode != 0 || gamma) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(jk_kernel<RMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    jk_kernel<RMAX, true><<<grid, 256, smem, st>>>(src, dst, B, C, I, J, K, bl, bi);
+    jk_kernel<RMAX, true><<<grid, 256, smem, st>>>(src, dst, B, C, I, J, K, bl, nz, gamma);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(jk_kernel<RMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    jk_kernel<RMAX, false><<<grid, 256, smem, st>>>(src, dst, B, C, I, J, K, bl, bi);
+    jk_kernel<RMAX, false><<<grid, 256, smem, st>>>(src, dst, B, C, I, J, K, bl, nz, gamma);
   }
   return 0;
 }
@@ -422,39 +441,45 @@ static int fused_impl(const float* src, float* dst, float* scratch, int B, int C
     bi.sc_i = up_scale(bi.si, I); bi.sc_j = up_scale(bi.sj, J); bi.sc_k = up_scale(bi.sk, K);
     TIO_CHECK_ARG((size_t)bi.si * bi.sj * bi.sk * 4 <= 64 * 1024, "%s: coarse bias grid too large", who);
   }
+  const bool need_i = (axes_mask & 1) != 0;
+  const bool need_march = !need_jk || need_i || bi.coarse != nullptr;
   const float* cur = src;
-  BiasArgs none{};  // bias is applied exactly once, in the first pass that runs
-  if (need_jk) {
-    const int64_t tiles = (int64_t)B * C * ((I + A_PLANES - 1) / A_PLANES);
-    TIO_CHECK_ARG(tiles <= 65535, "%s: batch too large for the blur grid", who);
-    BlurArgs jk = bl;
-    if (bl.R <= 6) launch_jk<6>(cur, scratch, B, C, I, J, K, jk, bi, st);
-    else launch_jk<16>(cur, scratch, B, C, I, J, K, jk, bi, st);
-    cur = scratch;
-    bi = none;
-  }
-  BlurArgs ib = bl;
-  if (!(axes_mask & 1)) ib.taps = nullptr;
-  const bool vec = (K % 4 == 0) && aligned16f(cur) && aligned16f(dst) &&
-                   (nz.mode != 1 || (aligned16f(nz.z) && (!nz.z2 || aligned16f(nz.z2))));
-  const int V = vec ? 4 : 1;
-  dim3 block(64, 4);
-  dim3 grid((K + 64 * V - 1) / (64 * V), (J + 3) / 4, B * C);
-  TIO_CHECK_ARG(grid.y <= 65535, "%s: J too large", who);
-  const int R = ib.taps ? ib.R : 0;
-  const int ns = bi.coarse ? bi.si * bi.sj * bi.sk : 0;
-  const size_t smem = ((size_t)((2 * R + 1 + 3) / 4 * 4) + (size_t)((ns + 3) / 4 * 4) +
-                       (ib.taps ? (size_t)(2 * R + 1) * 256 * V : 0)) * sizeof(float);
+  if (need_march) {
+    // pass 1: bias + I-conv (+ noise/gamma when it is the only pass)
+    BlurArgs ib = bl;
+    if (!need_i) ib.taps = nullptr;
+    NoiseArgs nz1 = need_jk ? NoiseArgs{} : nz;
+    const float* gamma1 = need_jk ? nullptr : gamma;
+    float* out = need_jk ? scratch : dst;
+    const bool vec = (K % 4 == 0) && aligned16f(cur) && aligned16f(out) &&
+                     (nz1.mode != 1 || (aligned16f(nz1.z) && (!nz1.z2 || aligned16f(nz1.z2))));
+    const int V = vec ? 4 : 1;
+    dim3 block(64, 4);
+    dim3 grid((K + 64 * V - 1) / (64 * V), (J + 3) / 4, B * C);
+    TIO_CHECK_ARG(grid.y <= 65535, "%s: J too large", who);
+    const int R = ib.taps ? ib.R : 0;
+    const int ns = bi.coarse ? bi.si * bi.sj * bi.sk : 0;
+    const size_t smem = ((size_t)((2 * R + 1 + 3) / 4 * 4) + (size_t)((ns + 3) / 4 * 4) +
+                         (ib.taps ? (size_t)(2 * R + 1) * 256 * V : 0)) * sizeof(float);
 #define TIO_LAUNCH_MARCH(VV, BB)                                                              \
   do {                                                                                        \
     if (smem > 48 * 1024)                                                                     \
       cudaFuncSetAttribute(march_kernel<VV, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            (int)smem);                                                        \
-    march_kernel<VV, BB><<<grid, block, smem, st>>>(cur, dst, B, C, I, J, K, ib, bi, nz, gamma); \
+    march_kernel<VV, BB><<<grid, block, smem, st>>>(cur, out, B, C, I, J, K, ib, bi, nz1, gamma1); \
   } while (0)
-  if (vec) { if (bi.coarse) TIO_LAUNCH_MARCH(4, true); else TIO_LAUNCH_MARCH(4, false); }
-  else { if (bi.coarse) TIO_LAUNCH_MARCH(1, true); else TIO_LAUNCH_MARCH(1, false); }
+    if (vec) { if (bi.coarse) TIO_LAUNCH_MARCH(4, true); else TIO_LAUNCH_MARCH(4, false); }
+    else { if (bi.coarse) TIO_LAUNCH_MARCH(1, true); else TIO_LAUNCH_MARCH(1, false); }
 #undef TIO_LAUNCH_MARCH
+    cur = out;
+  }
+  if (need_jk) {
+    // pass 2: K-conv, J-conv, then noise and gamma at the store
+    const int64_t tiles = (int64_t)B * C * ((I + A_PLANES - 1) / A_PLANES);
+    TIO_CHECK_ARG(tiles <= 65535, "%s: batch too large for the blur grid", who);
+    if (bl.R <= 6) launch_jk<6>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
+    else launch_jk<16>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
+  }
   TIO_CHECK_LAUNCH();
   return 0;
 }

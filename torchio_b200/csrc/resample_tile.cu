@@ -42,6 +42,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+template <int OFFSET>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFFSET));
+  return v;
+}
+
 template <bool FASTDIV>
 __device__ __forceinline__ float norm_div(float x, float hd, float rcp) {
   if (FASTDIV) {
@@ -95,30 +102,257 @@ __device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts
   return n;
 }
 
+// ---------------------------------------------------------------------------
+// pre-pass: one warp per output tile bounds the tile's pre-image and records
+// (box origin, fit code) so the main kernel can issue its TMA load at once.
+//   code 0: does not fit the box -> general path     code 1: fits
+//   code 2: pre-image entirely outside the volume    bit 8: every tap in bounds
+// ---------------------------------------------------------------------------
+template <bool HAS_CP>
+__global__ void __launch_bounds__(256)
+tile_bounds_kernel(const ResampleArgs a, const int box, int4* __restrict__ records) {
+  const int lane = threadIdx.x & 31;
+  const int tiles_i = (a.OI + XT - 1) / XT, tiles_j = (a.OJ + XT - 1) / XT, tiles_k = (a.OK + XT - 1) / XT;
+  const int64_t n_tiles = (int64_t)a.B * tiles_i * tiles_j * tiles_k;
+  const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const int tk = (int)(tile % tiles_k), tj = (int)((tile / tiles_k) % tiles_j);
+  const int ti = (int)((tile / ((int64_t)tiles_k * tiles_j)) % tiles_i);
+  const int b = (int)(tile / ((int64_t)tiles_k * tiles_j * tiles_i));
+  const int i0 = ti * XT, j0 = tj * XT, k0 = tk * XT;
+  const int i1 = min(i0 + XT, a.OI) - 1, j1 = min(j0 + XT, a.OJ) - 1, k1 = min(k0 + XT, a.OK) - 1;
+  const uint8_t fl = a.flags ? a.flags[b] : 0;
+  if (fl & TIO_FLAG_PASSTHROUGH) {
+    if (lane == 0) records[tile] = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const bool elastic = HAS_CP && (fl & TIO_FLAG_ELASTIC);
+  float dmn[3] = {0.f, 0.f, 0.f}, dmx[3] = {0.f, 0.f, 0.f};
+  bool ok_bounds = true;
+  if (elastic) {
+    const float* g = a.cp + (int64_t)b * a.ni * a.nj * a.nk * 3;
+    int pi[12], pj[12], pk[12];
+    const int ni_ = axis_points(a.sc_i, i0, i1, pi);
+    const int nj_ = axis_points(a.sc_j, j0, j1, pj);
+    const int nk_ = axis_points(a.sc_k, k0, k1, pk);
+    if (ni_ < 0 || nj_ < 0 || nk_ < 0) {
+      ok_bounds = false;
+    } else {
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) { dmn[ax] = 3.0e38f; dmx[ax] = -3.0e38f; }
+      const int total = ni_ * nj_ * nk_;
+      for (int t = lane; t < total; t += 32) {
+        const int qk = t % nk_, qj = (t / nk_) % nj_, qi = t / (nk_ * nj_);
+        float d[3];
+        disp_at(g, a, pi[qi], pj[qj], pk[qk], d);
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) { dmn[ax] = fminf(dmn[ax], d[ax]); dmx[ax] = fmaxf(dmx[ax], d[ax]); }
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          dmn[ax] = fminf(dmn[ax], __shfl_xor_sync(0xffffffffu, dmn[ax], s));
+          dmx[ax] = fmaxf(dmx[ax], __shfl_xor_sync(0xffffffffu, dmx[ax], s));
+        }
+    }
+  }
+  if (lane != 0) return;
+  const float* m = a.mat + b * 12;
+  const int dims[3] = {a.I, a.J, a.K};
+  const float plo[3] = {(float)i0, (float)j0, (float)k0};
+  const float phi[3] = {(float)i1, (float)j1, (float)k1};
+  float elo[3], ehi[3], add_lo[3] = {0.f, 0.f, 0.f}, add_hi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) { elo[ax] = plo[ax]; ehi[ax] = phi[ax]; }
+  if (elastic) {
+    if (a.affine_first) {
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) { add_lo[ax] = dmn[ax] / a.sp_in[ax]; add_hi[ax] = dmx[ax] / a.sp_in[ax]; }
+    } else {
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) { elo[ax] += dmn[ax] / a.sp_out[ax]; ehi[ax] += dmx[ax] / a.sp_out[ax]; }
+    }
+  }
+  bool fits = ok_bounds, interior = true, outside = false;
+  int ilo[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    float qlo = m[4 * ax + 3], qhi = m[4 * ax + 3];
+#pragma unroll
+    for (int bx = 0; bx < 3; ++bx) {
+      const float v0 = m[4 * ax + bx] * elo[bx], v1 = m[4 * ax + bx] * ehi[bx];
+      qlo += fminf(v0, v1);
+      qhi += fmaxf(v0, v1);
+    }
+    qlo += add_lo[ax];
+    qhi += add_hi[ax];
+    const float margin = 0.02f + 1e-5f * fmaxf(fabsf(qlo), fabsf(qhi));
+    qlo -= margin;
+    qhi += margin;
+    if (dims[ax] == 1) { qlo = 0.0f; qhi = 0.0f; }  // (size-1) == 0 collapses the axis
+    if (!(fabsf(qlo) < 1.0e6f && fabsf(qhi) < 1.0e6f)) { fits = false; qlo = 0.f; qhi = 0.f; }
+    int lo = (int)floorf(qlo), hi = (int)floorf(qhi) + 1;
+    // every corner (floor(u), floor(u)+1) out of bounds on this axis => all padding
+    if (hi < 0 || lo > dims[ax] - 1) outside = true;
+    if (ax == 2) lo &= ~3;  // TMA: innermost coordinate must be 16-byte aligned
+    if (hi - lo + 1 > (ax == 2 ? box + 4 : box)) fits = false;
+    if (lo < 0 || hi > dims[ax] - 1) interior = false;
+    ilo[ax] = lo;
+  }
+  const int code = (ok_bounds && outside) ? 2 : (fits ? 1 : 0);
+  records[tile] = make_int4(ilo[0], ilo[1], ilo[2], code | (interior ? 256 : 0));
+}
+
+struct LiEntry {  // per output plane of the tile: I-axis lerp of the control grid
+  int off0, off1;  // i0 * plane, i1 * plane (floats)
+  float l0, l1;
+};
+
+// The 16-plane walk of one (j,k) column over the staged box.  CHECK = the tile
+// touches the volume border and a fill value is set: per-voxel ATen mask.
+template <int BOX, bool HAS_CP, bool CHECK, bool FASTDIV>
+__device__ __forceinline__ void walk_column(
+    const ResampleArgs& a, const TileArgs& ta, const float* __restrict__ box,
+    const float* __restrict__ cps, const LiEntry* __restrict__ li_tab, const float m[12],
+    const bool elastic, const bool identity, const uint32_t kbase, const int i0, const int i1,
+    const int oj, const int ok, const float fill_c, float* __restrict__ out, const int64_t ostride) {
+  constexpr int BK = BOX + 4;
+  constexpr int C1 = BOX * BK, C2 = BK;
+  const float hd0 = ta.hd[0], hd1 = ta.hd[1], hd2 = ta.hd[2];
+  const float rc0 = ta.rcp[0], rc1 = ta.rcp[1], rc2 = ta.rcp[2];
+  const float hs0 = ta.hs[0], hs1 = ta.hs[1], hs2 = ta.hs[2];
+  const float pj = (float)oj, pk = (float)ok;
+  // J/K levels of the nested displacement lerp, cached across the walk
+  LerpAxis lj, lk;
+  int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+  if (HAS_CP && elastic) {
+    lj = lerp_axis(a.sc_j, a.nj, oj);
+    lk = lerp_axis(a.sc_k, a.nk, ok);
+    o00 = (lj.i0 * a.nk + lk.i0) * 3; o01 = (lj.i0 * a.nk + lk.i1) * 3;
+    o10 = (lj.i1 * a.nk + lk.i0) * 3; o11 = (lj.i1 * a.nk + lk.i1) * 3;
+  }
+  int cur0 = -1, cur1 = -1;
+  float r_lo[3] = {0.f, 0.f, 0.f}, r_hi[3] = {0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int oi = i0; oi <= i1; ++oi, out += ostride) {
+    const float pi = (float)oi;
+    float q0, q1, q2;
+    if (HAS_CP && elastic) {
+      const LiEntry li = li_tab[oi - i0];  // warp-uniform broadcast
+      if (li.off0 != cur0 || li.off1 != cur1) {
+        const float* p0 = cps + li.off0;
+        const float* p1 = cps + li.off1;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
+          float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
+          r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
+          float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
+          float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
+          r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
+        }
+        cur0 = li.off0; cur1 = li.off1;
+      }
+      float d0 = lerp2(li.l0, r_lo[0], li.l1, r_hi[0]);
+      float d1 = lerp2(li.l0, r_lo[1], li.l1, r_hi[1]);
+      float d2 = lerp2(li.l0, r_lo[2], li.l1, r_hi[2]);
+      if (a.affine_first) {
+        if (!ta.sp_in_one) { d0 = __fdiv_rn(d0, a.sp_in[0]); d1 = __fdiv_rn(d1, a.sp_in[1]); d2 = __fdiv_rn(d2, a.sp_in[2]); }
+        if (identity) {  // [p,1] @ I^T == p exactly
+          q0 = __fadd_rn(pi, d0); q1 = __fadd_rn(pj, d1); q2 = __fadd_rn(pk, d2);
+        } else {
+          q0 = __fadd_rn(affine_row(m + 0, pi, pj, pk), d0);
+          q1 = __fadd_rn(affine_row(m + 4, pi, pj, pk), d1);
+          q2 = __fadd_rn(affine_row(m + 8, pi, pj, pk), d2);
+        }
+      } else {
+        if (!ta.sp_out_one) { d0 = __fdiv_rn(d0, a.sp_out[0]); d1 = __fdiv_rn(d1, a.sp_out[1]); d2 = __fdiv_rn(d2, a.sp_out[2]); }
+        const float e0 = __fadd_rn(pi, d0), e1 = __fadd_rn(pj, d1), e2 = __fadd_rn(pk, d2);
+        q0 = affine_row(m + 0, e0, e1, e2);
+        q1 = affine_row(m + 4, e0, e1, e2);
+        q2 = affine_row(m + 8, e0, e1, e2);
+      }
+    } else {
+      q0 = affine_row(m + 0, pi, pj, pk);
+      q1 = affine_row(m + 4, pi, pj, pk);
+      q2 = affine_row(m + 8, pi, pj, pk);
+    }
+    // 2q/nm1 - 1  ->  ((g+1)/2)*(size-1), as rn(q/hd), -1, +1, *hs (exact rescalings)
+    const float u0 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q0, hd0, rc0), 1.0f), 1.0f), hs0);
+    const float u1 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q1, hd1, rc1), 1.0f), 1.0f), hs1);
+    const float u2 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q2, hd2, rc2), 1.0f), 1.0f), hs2);
+    // floor via round-down magic add: the mantissa holds floor(u)
+    const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
+    const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2 = __fsub_rn(s2, kMagic);
+    const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2);
+    const int b0 = __float_as_int(s0), b1 = __float_as_int(s1), b2 = __float_as_int(s2);
+    // byte address of tap (floor i, floor j, floor k): one base register, the other
+    // seven taps are compile-time immediates off it
+    const uint32_t addr = kbase + (((unsigned)b0 * C1 + (unsigned)b1 * C2 + (unsigned)b2) << 2);
+    bool use_fill = false;
+    if (CHECK) {
+      const int c0 = b0 - kMagicBits, c1 = b1 - kMagicBits, c2 = b2 - kMagicBits;
+      const bool vox_interior = ((unsigned)c0 < (unsigned)(a.I - 1)) & ((unsigned)c1 < (unsigned)(a.J - 1)) &
+                                ((unsigned)c2 < (unsigned)(a.K - 1));
+      if (!vox_interior) {  // exact ATen mask: ordered sum of the in-bounds corner weights
+        const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
+                    lo2 = __fsub_rn(__fadd_rn(f2, 1.0f), u2);
+        const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
+        const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
+        const bool il = (unsigned)c0 < (unsigned)a.I, ih = (unsigned)(c0 + 1) < (unsigned)a.I;
+        const bool jl = (unsigned)c1 < (unsigned)a.J, jh = (unsigned)(c1 + 1) < (unsigned)a.J;
+        const bool kl = (unsigned)c2 < (unsigned)a.K, kh = (unsigned)(c2 + 1) < (unsigned)a.K;
+        float msum = 0.0f;
+        if (il & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w00, lo2));
+        if (ih & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w10, lo2));
+        if (il & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w01, lo2));
+        if (ih & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w11, lo2));
+        if (il & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w00, hi2));
+        if (ih & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w10, hi2));
+        if (il & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w01, hi2));
+        if (ih & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w11, hi2));
+        use_fill = !(msum > 0.5f);
+      }
+    }
+    // separable lerp K -> J -> I over the zero-padded box (<= 1 ulp from ATen's 8-term
+    // weighted sum; the zero halo == skipping out-of-bounds corners)
+    const float v000 = lds_f32<0>(addr), v001 = lds_f32<4>(addr);
+    const float v010 = lds_f32<4 * C2>(addr), v011 = lds_f32<4 * C2 + 4>(addr);
+    const float v100 = lds_f32<4 * C1>(addr), v101 = lds_f32<4 * C1 + 4>(addr);
+    const float v110 = lds_f32<4 * (C1 + C2)>(addr), v111 = lds_f32<4 * (C1 + C2) + 4>(addr);
+    const float a00 = __fmaf_rn(hi2, v001 - v000, v000);
+    const float a01 = __fmaf_rn(hi2, v011 - v010, v010);
+    const float a10 = __fmaf_rn(hi2, v101 - v100, v100);
+    const float a11 = __fmaf_rn(hi2, v111 - v110, v110);
+    const float bb0 = __fmaf_rn(hi1, a01 - a00, a00);
+    const float bb1 = __fmaf_rn(hi1, a11 - a10, a10);
+    float v = __fmaf_rn(hi0, bb1 - bb0, bb0);
+    if (CHECK && use_fill) v = fill_c;
+    *out = v;
+  }
+}
+
 template <int BOX, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
 __global__ void __launch_bounds__(256)
 resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArgs a,
-                     const TileArgs ta) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [box: BOX^3 floats | cp: ncp floats | ctl]
-  float* box = (float*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+                     const TileArgs ta, const int4* __restrict__ records) {
   constexpr int BK = BOX + 4;  // inner (K) box extent: room for the 16-byte origin alignment
-  float* cps = box + BOX * BOX * BK;
+  constexpr int NBOX = BOX * BOX * BK;
+  // layout: [box floats | li table (16 entries) | mbarrier | cp floats]
+  extern __shared__ __align__(128) float smem[];
+  float* box = smem;
+  LiEntry* li_tab = reinterpret_cast<LiEntry*>(smem + NBOX);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + NBOX + 64);  // [+66] = kbase
+  float* cps = smem + NBOX + 64 + 4;
   const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
-  struct Ctl {
-    unsigned long long bar;
-    int ilo[3];
-    int fits, interior;
-    float dmin[3], dmax[3];
-  };
-  Ctl* ctl = (Ctl*)(((uintptr_t)(cps + ncp) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x;
   const int tiles_i = (a.OI + XT - 1) / XT;
   const int b = blockIdx.z / tiles_i;
-  const int i0 = (blockIdx.z % tiles_i) * XT;
-  const int j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
-  const int i1 = min(i0 + XT, a.OI) - 1, j1 = min(j0 + XT, a.OJ) - 1, k1 = min(k0 + XT, a.OK) - 1;
+  const int ti = blockIdx.z % tiles_i;
+  const int i0 = ti * XT, j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
+  const int i1 = min(i0 + XT, a.OI) - 1;
   // lanes 0-15 / 16-31 of a warp take rows DJ apart: with row pitch BK the two
   // half-warps then hit disjoint banks (DJ * BK == 16 mod 32) for axis-aligned reads
   constexpr int DJ = (BOX == 20) ? 2 : 4;
@@ -140,100 +374,12 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
         }
     return;
   }
+  const int64_t tile_id = (((int64_t)b * tiles_i + ti) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int4 rec = __ldg(records + tile_id);
+  const int fit_code = rec.w & 255;
+  const bool tile_interior = (rec.w & 256) != 0;
   const bool elastic = HAS_CP && (fl & TIO_FLAG_ELASTIC);
-  if (elastic) {
-    const float* gsrc = a.cp + (int64_t)b * ncp;
-    for (int t = tid; t < ncp; t += 256) cps[t] = gsrc[t];
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ctl->bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
 
-  float m[12];
-#pragma unroll
-  for (int t = 0; t < 12; ++t) m[t] = a.mat[b * 12 + t];
-  const int dims[3] = {a.I, a.J, a.K};
-
-  // ---------------- warp 0: bound the tile's pre-image ----------------
-  if (tid < 32) {
-    float dmn[3] = {0.f, 0.f, 0.f}, dmx[3] = {0.f, 0.f, 0.f};
-    bool ok_bounds = true;
-    if (elastic) {
-      int pi[12], pj[12], pk[12];
-      const int ni_ = axis_points(a.sc_i, i0, i1, pi);
-      const int nj_ = axis_points(a.sc_j, j0, j1, pj);
-      const int nk_ = axis_points(a.sc_k, k0, k1, pk);
-      if (ni_ < 0 || nj_ < 0 || nk_ < 0) {
-        ok_bounds = false;
-      } else {
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) { dmn[ax] = 3.0e38f; dmx[ax] = -3.0e38f; }
-        const int total = ni_ * nj_ * nk_;
-        for (int t = tid; t < total; t += 32) {
-          const int tk = t % nk_, tj = (t / nk_) % nj_, ti = t / (nk_ * nj_);
-          float d[3];
-          disp_at(cps, a, pi[ti], pj[tj], pk[tk], d);
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) { dmn[ax] = fminf(dmn[ax], d[ax]); dmx[ax] = fmaxf(dmx[ax], d[ax]); }
-        }
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1)
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            dmn[ax] = fminf(dmn[ax], __shfl_xor_sync(0xffffffffu, dmn[ax], s));
-            dmx[ax] = fmaxf(dmx[ax], __shfl_xor_sync(0xffffffffu, dmx[ax], s));
-          }
-      }
-    }
-    if (tid == 0) {
-      const float plo[3] = {(float)i0, (float)j0, (float)k0};
-      const float phi[3] = {(float)i1, (float)j1, (float)k1};
-      float elo[3], ehi[3], add_lo[3] = {0.f, 0.f, 0.f}, add_hi[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) { elo[ax] = plo[ax]; ehi[ax] = phi[ax]; }
-      if (elastic) {
-        if (a.affine_first) {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) { add_lo[ax] = dmn[ax] / a.sp_in[ax]; add_hi[ax] = dmx[ax] / a.sp_in[ax]; }
-        } else {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) { elo[ax] += dmn[ax] / a.sp_out[ax]; ehi[ax] += dmx[ax] / a.sp_out[ax]; }
-        }
-      }
-      bool fits = ok_bounds, interior = true, outside = false;
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        float qlo = m[4 * ax + 3], qhi = m[4 * ax + 3];
-#pragma unroll
-        for (int bx = 0; bx < 3; ++bx) {
-          const float v0 = m[4 * ax + bx] * elo[bx], v1 = m[4 * ax + bx] * ehi[bx];
-          qlo += fminf(v0, v1);
-          qhi += fmaxf(v0, v1);
-        }
-        qlo += add_lo[ax];
-        qhi += add_hi[ax];
-        const float margin = 0.02f + 1e-5f * fmaxf(fabsf(qlo), fabsf(qhi));
-        qlo -= margin;
-        qhi += margin;
-        if (dims[ax] == 1) { qlo = 0.0f; qhi = 0.0f; }  // (size-1) == 0 collapses the axis
-        if (!(fabsf(qlo) < 1.0e6f && fabsf(qhi) < 1.0e6f)) { fits = false; qlo = 0.f; qhi = 0.f; }
-        int lo = (int)floorf(qlo), hi = (int)floorf(qhi) + 1;
-        // every corner (floor(u), floor(u)+1) out of bounds on this axis => the
-        // whole tile is padding: value 0, mask 0
-        if (hi < 0 || lo > dims[ax] - 1) outside = true;
-        if (ax == 2) lo &= ~3;  // TMA: innermost coordinate must be 16-byte aligned
-        if (hi - lo + 1 > (ax == 2 ? BK : BOX)) fits = false;
-        if (lo < 0 || hi > dims[ax] - 1) interior = false;
-        ctl->ilo[ax] = lo;
-      }
-      ctl->fits = (ok_bounds && outside) ? 2 : (fits ? 1 : 0);
-      ctl->interior = interior ? 1 : 0;
-    }
-  }
-  __syncthreads();
-  const int fit_code = ctl->fits;
   if (fit_code == 2) {  // pre-image entirely outside the volume
     if (active)
       for (int c = 0; c < a.C; ++c) {
@@ -243,48 +389,69 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
       }
     return;
   }
+  if (tid == 0 && fit_code == 1) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first channel's box: in flight while the CTA stages the control grid
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"((uint32_t)(NBOX * sizeof(float)))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(box)),
+        "l"((unsigned long long)&tmap), "r"(rec.z), "r"(rec.y), "r"(rec.x), "r"(b * a.C), "r"(smem_u32(bar))
+        : "memory");
+  }
+  if (tid == 32) {
+    constexpr int C1 = BOX * BK, C2 = BK;
+    const unsigned koff = (unsigned)(kMagicBits + rec.x) * C1 + (unsigned)(kMagicBits + rec.y) * C2 +
+                          (unsigned)(kMagicBits + rec.z);
+    *reinterpret_cast<uint32_t*>(smem + NBOX + 66) = smem_u32(box) - (koff << 2);
+  }
+  if (elastic) {
+    const float* gsrc = a.cp + (int64_t)b * ncp;
+    for (int t = tid; t < ncp; t += 256) cps[t] = gsrc[t];
+    if (tid < XT) {
+      const LerpAxis li = lerp_axis(a.sc_i, a.ni, min(i0 + tid, a.OI - 1));
+      const int plane = a.nj * a.nk * 3;
+      li_tab[tid] = LiEntry{li.i0 * plane, li.i1 * plane, li.l0, li.l1};
+    }
+  }
+  __syncthreads();  // mbarrier init + control grid + li table visible
+
   if (fit_code == 0) {  // general global-memory path for this tile (CTA-uniform branch)
     if (active)
       general_column<float, TIO_LINEAR, HAS_CP, HAS_FILL>(a, b, elastic, elastic ? cps : nullptr, src,
                                                           dst, n_in, n_out, i0, i1 + 1, oj, ok);
     return;
   }
-  const int ilo0 = ctl->ilo[0], ilo1 = ctl->ilo[1], ilo2 = ctl->ilo[2];
-  const bool tile_interior = ctl->interior != 0;
 
-  // per-thread displacement state (J/K levels cached across the I walk)
-  LerpAxis lj, lk;
-  int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-  if (elastic && active) {
-    lj = lerp_axis(a.sc_j, a.nj, oj);
-    lk = lerp_axis(a.sc_k, a.nk, ok);
-    o00 = (lj.i0 * a.nk + lk.i0) * 3; o01 = (lj.i0 * a.nk + lk.i1) * 3;
-    o10 = (lj.i1 * a.nk + lk.i0) * 3; o11 = (lj.i1 * a.nk + lk.i1) * 3;
-  }
-  const int plane = a.nj * a.nk * 3;
-  const float pj = (float)oj, pk = (float)ok;
+  float m[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) m[t] = a.mat[b * 12 + t];
   constexpr int C1 = BOX * BK, C2 = BK;
-  const unsigned koff = (unsigned)(kMagicBits + ilo0) * C1 + (unsigned)(kMagicBits + ilo1) * C2 +
-                        (unsigned)(kMagicBits + ilo2);
-  const bool identity = !elastic ? false
-                                 : (m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f &&
-                                    m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[7] == 0.f &&
-                                    m[8] == 0.f && m[9] == 0.f && m[10] == 1.f && m[11] == 0.f);
+  // wraps; undone by the per-voxel sum.  Read back through shared memory so ptxas sees
+  // an opaque value (it otherwise splits off the 0x4B400000*(C1+C2+1) part and re-adds
+  // it in front of each of the 8 taps)
+  const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(smem + NBOX + 66);
+  const bool identity = elastic && m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f &&
+                        m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[7] == 0.f && m[8] == 0.f &&
+                        m[9] == 0.f && m[10] == 1.f && m[11] == 0.f;
+  const int64_t ostride = (int64_t)a.OJ * a.OK;
 
   for (int c = 0; c < a.C; ++c) {
-    if (tid == 0) {
-      const uint32_t bar = smem_u32(&ctl->bar);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                   "r"((uint32_t)(BOX * BOX * BK * sizeof(float)))
+    if (c > 0 && tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                   "r"((uint32_t)(NBOX * sizeof(float)))
                    : "memory");
       asm volatile(
           "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
           " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(box)),
-          "l"((unsigned long long)&tmap), "r"(ilo2), "r"(ilo1), "r"(ilo0), "r"(b * a.C + c), "r"(bar)
+          "l"((unsigned long long)&tmap), "r"(rec.z), "r"(rec.y), "r"(rec.x), "r"(b * a.C + c),
+          "r"(smem_u32(bar))
           : "memory");
     }
     {  // wait for the box (phase parity = c & 1)
-      const uint32_t bar = smem_u32(&ctl->bar);
       const uint32_t parity = (uint32_t)(c & 1);
       uint32_t done;
       do {
@@ -295,115 +462,18 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
       } while (!done);
     }
     if (active) {
-      int cur_i0 = -1, cur_i1 = -1;
-      float r_lo[3] = {0.f, 0.f, 0.f}, r_hi[3] = {0.f, 0.f, 0.f};
       float* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
-      const int64_t ostride = (int64_t)a.OJ * a.OK;
-#pragma unroll 2
-      for (int oi = i0; oi <= i1; ++oi, out += ostride) {
-        const float pi = (float)oi;
-        float q0, q1, q2;
-        if (HAS_CP && elastic) {
-          const LerpAxis li = lerp_axis(a.sc_i, a.ni, oi);
-          if (li.i0 != cur_i0 || li.i1 != cur_i1) {
-            const float* p0 = cps + li.i0 * plane;
-            const float* p1 = cps + li.i1 * plane;
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-              float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
-              float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
-              r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
-              float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
-              float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
-              r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
-            }
-            cur_i0 = li.i0; cur_i1 = li.i1;
-          }
-          float d0 = lerp2(li.l0, r_lo[0], li.l1, r_hi[0]);
-          float d1 = lerp2(li.l0, r_lo[1], li.l1, r_hi[1]);
-          float d2 = lerp2(li.l0, r_lo[2], li.l1, r_hi[2]);
-          if (a.affine_first) {
-            if (!ta.sp_in_one) { d0 = __fdiv_rn(d0, a.sp_in[0]); d1 = __fdiv_rn(d1, a.sp_in[1]); d2 = __fdiv_rn(d2, a.sp_in[2]); }
-            if (identity) {  // [p,1] @ I^T == p exactly
-              q0 = __fadd_rn(pi, d0); q1 = __fadd_rn(pj, d1); q2 = __fadd_rn(pk, d2);
-            } else {
-              q0 = __fadd_rn(affine_row(m + 0, pi, pj, pk), d0);
-              q1 = __fadd_rn(affine_row(m + 4, pi, pj, pk), d1);
-              q2 = __fadd_rn(affine_row(m + 8, pi, pj, pk), d2);
-            }
-          } else {
-            if (!ta.sp_out_one) { d0 = __fdiv_rn(d0, a.sp_out[0]); d1 = __fdiv_rn(d1, a.sp_out[1]); d2 = __fdiv_rn(d2, a.sp_out[2]); }
-            const float e0 = __fadd_rn(pi, d0), e1 = __fadd_rn(pj, d1), e2 = __fadd_rn(pk, d2);
-            q0 = affine_row(m + 0, e0, e1, e2);
-            q1 = affine_row(m + 4, e0, e1, e2);
-            q2 = affine_row(m + 8, e0, e1, e2);
-          }
-        } else {
-          q0 = affine_row(m + 0, pi, pj, pk);
-          q1 = affine_row(m + 4, pi, pj, pk);
-          q2 = affine_row(m + 8, pi, pj, pk);
-        }
-        // 2q/nm1 - 1  ->  ((g+1)/2)*(size-1), as rn(q/hd), -1, +1, *hs (all exact rescalings)
-        const float u0 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q0, ta.hd[0], ta.rcp[0]), 1.0f), 1.0f), ta.hs[0]);
-        const float u1 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q1, ta.hd[1], ta.rcp[1]), 1.0f), 1.0f), ta.hs[1]);
-        const float u2 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q2, ta.hd[2], ta.rcp[2]), 1.0f), 1.0f), ta.hs[2]);
-        // floor via round-down magic add: mantissa holds floor(u)
-        const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
-        const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2 = __fsub_rn(s2, kMagic);
-        const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2);
-        const int b0 = __float_as_int(s0), b1 = __float_as_int(s1), b2 = __float_as_int(s2);
-        const int off = (int)((unsigned)b0 * C1 + (unsigned)b1 * C2 + (unsigned)b2 - koff);
-        const float* p = box + off;
-        float v;
-        bool use_fill = false;
-        if (HAS_FILL && !tile_interior) {
-          const int c0 = b0 - kMagicBits, c1 = b1 - kMagicBits, c2 = b2 - kMagicBits;
-          const bool vox_interior = (c0 >= 0) & (c0 + 1 < a.I) & (c1 >= 0) & (c1 + 1 < a.J) &
-                                    (c2 >= 0) & (c2 + 1 < a.K);
-          if (!vox_interior) {  // exact ATen mask: ordered sum of in-bounds corner weights
-            const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
-                        lo2 = __fsub_rn(__fadd_rn(f2, 1.0f), u2);
-            const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
-            const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
-            const bool il = (c0 >= 0) & (c0 < a.I), ih = (c0 + 1 >= 0) & (c0 + 1 < a.I);
-            const bool jl = (c1 >= 0) & (c1 < a.J), jh = (c1 + 1 >= 0) & (c1 + 1 < a.J);
-            const bool kl = (c2 >= 0) & (c2 < a.K), kh = (c2 + 1 >= 0) & (c2 + 1 < a.K);
-            float msum = 0.0f;
-            if (il & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w00, lo2));
-            if (ih & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w10, lo2));
-            if (il & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w01, lo2));
-            if (ih & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w11, lo2));
-            if (il & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w00, hi2));
-            if (ih & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w10, hi2));
-            if (il & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w01, hi2));
-            if (ih & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w11, hi2));
-            use_fill = !(msum > 0.5f);
-          }
-        }
-        if (HAS_FILL && use_fill) {
-          v = a.fill[c];
-        } else {
-          // separable lerp K -> J -> I over the zero-padded box (<= 1 ulp from ATen's
-          // 8-term weighted sum; zero halo == skipping out-of-bounds corners)
-          const float v000 = p[0], v001 = p[1];
-          const float v010 = p[C2], v011 = p[C2 + 1];
-          const float v100 = p[C1], v101 = p[C1 + 1];
-          const float v110 = p[C1 + C2], v111 = p[C1 + C2 + 1];
-          const float a00 = __fmaf_rn(hi2, v001 - v000, v000);
-          const float a01 = __fmaf_rn(hi2, v011 - v010, v010);
-          const float a10 = __fmaf_rn(hi2, v101 - v100, v100);
-          const float a11 = __fmaf_rn(hi2, v111 - v110, v110);
-          const float bb0 = __fmaf_rn(hi1, a01 - a00, a00);
-          const float bb1 = __fmaf_rn(hi1, a11 - a10, a10);
-          v = __fmaf_rn(hi0, bb1 - bb0, bb0);
-        }
-        *out = v;
-      }
+      if (HAS_FILL && !tile_interior)
+        walk_column<BOX, HAS_CP, true, FASTDIV>(a, ta, box, cps, li_tab, m, elastic, identity, kbase, i0,
+                                               i1, oj, ok, a.fill[c], out, ostride);
+      else
+        walk_column<BOX, HAS_CP, false, FASTDIV>(a, ta, box, cps, li_tab, m, elastic, identity, kbase, i0,
+                                                i1, oj, ok, 0.0f, out, ostride);
     }
     if (c + 1 < a.C) __syncthreads();  // box is reused by the next channel
   }
@@ -476,27 +546,27 @@ static EncodeTiledFn encode_tiled_fn() {
 
 template <int BOX, bool HAS_CP, bool FASTDIV>
 static void launch_tile(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
-                        size_t smem, cudaStream_t st) {
+                        size_t smem, const int4* records, cudaStream_t st) {
   if (a.fill) {
     cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, true, FASTDIV>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_tile_kernel<BOX, HAS_CP, true, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta);
+    resample_tile_kernel<BOX, HAS_CP, true, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
   } else {
     cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, false, FASTDIV>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_tile_kernel<BOX, HAS_CP, false, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta);
+    resample_tile_kernel<BOX, HAS_CP, false, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
   }
 }
 
 template <int BOX>
 static void launch_box(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
-                       size_t smem, bool fast, cudaStream_t st) {
+                       size_t smem, bool fast, const int4* records, cudaStream_t st) {
   if (a.cp) {
-    if (fast) launch_tile<BOX, true, true>(tm, a, ta, grid, smem, st);
-    else launch_tile<BOX, true, false>(tm, a, ta, grid, smem, st);
+    if (fast) launch_tile<BOX, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<BOX, true, false>(tm, a, ta, grid, smem, records, st);
   } else {
-    if (fast) launch_tile<BOX, false, true>(tm, a, ta, grid, smem, st);
-    else launch_tile<BOX, false, false>(tm, a, ta, grid, smem, st);
+    if (fast) launch_tile<BOX, false, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<BOX, false, false>(tm, a, ta, grid, smem, records, st);
   }
 }
 
@@ -538,10 +608,17 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
   ta.sp_out_one = (a.sp_out[0] == 1.f && a.sp_out[1] == 1.f && a.sp_out[2] == 1.f);
 
   dim3 grid((a.OK + XT - 1) / XT, (a.OJ + XT - 1) / XT, (unsigned)(a.B * tiles_i));
-  const size_t smem = 128 + (size_t)box * box * (box + 4) * 4 + ncp * 4 + 16 + 64;
-  if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, st);
-  else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, st);
-  else launch_box<32>(tm, a, ta, grid, smem, fast, st);
+  const int64_t n_tiles = (int64_t)grid.x * grid.y * grid.z;
+  int4* records = nullptr;  // stream-ordered scratch: no state survives the call
+  if (cudaMallocAsync((void**)&records, (size_t)n_tiles * sizeof(int4), st) != cudaSuccess) return 1;
+  const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
+  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, records);
+  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, records);
+  const size_t smem = ((size_t)box * box * (box + 4) + 64 + 4 + ncp) * sizeof(float);
+  if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);
+  else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, records, st);
+  else launch_box<32>(tm, a, ta, grid, smem, fast, records, st);
+  cudaFreeAsync(records, st);
   return 0;
 }
 

@@ -170,8 +170,14 @@ def blur(src: Tensor, taps: Tensor, radius: Tensor, big_r: int, axes_mask: int,
             "tio_blur", _ptr(src), _ptr(dst), _ptr(scratch), b, c, i, j, k, _ptr(taps),
             _ptr(radius), int(big_r), int(axes_mask), _ptr(identity), _stream(src),
         )
-    _count(2 if (axes_mask & 6) else 1)
+    _count(_fused_launches(axes_mask, False))
     return dst
+
+
+def _fused_launches(axes_mask: int, has_bias: bool) -> int:
+    jk = bool(axes_mask & 6)
+    march = (not jk) or bool(axes_mask & 1) or has_bias
+    return int(jk) + int(march)
 
 
 def noise(src: Tensor, mean: Tensor, std: Tensor, keep: Tensor | None, z: Tensor,
@@ -249,5 +255,5 @@ def intensity_fused(
             int(philox_seed) & (2**64 - 1), int(noise_mode), int(bool(rician)),
             _ptr(gamma), _stream(src),
         )
-    _count(2 if jk else 1)
+    _count(_fused_launches(axes_mask if taps is not None else 0, coarse is not None))
     return dst
