@@ -37,8 +37,8 @@ ALGO_BYTES_PER_VOXEL_RESAMPLE = 8  # one fp32 read + one fp32 write (SURVEY.md Â
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="full", choices=["full", "config2"])
     ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
@@ -104,16 +104,26 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=10.0):
+        """nvidia-smi takes a while to start: do not let its start-up overlap the timed region."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        window = [l for t, l in self.lines
+                  if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.25)]
+        if not window:  # region shorter than the sampling period: take the nearest samples
+            window = [l for _, l in self.lines[-2:]]
+        for line in window:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -183,24 +193,28 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    torch.manual_seed(1234 + rank)
-    for _ in range(args.warmup):
-        out = step(resident)
-    k1_events.clear()
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    torch.manual_seed(1234 + rank)
+    for _ in range(args.warmup):
+        out = step(resident)
+    if sampler:
+        sampler.wait_first_sample()
+    k1_events.clear()
+    barrier()
     launches0 = ops.launches()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall_begin = time.perf_counter()
     t0.record()
     for _ in range(args.steps):
         out = step(resident)
     t1.record()
     barrier()
+    wall_end = time.perf_counter()
     ms = t0.elapsed_time(t1)
     launches = ops.launches() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall_begin, wall_end) if sampler else None
     k1_ms = [s.elapsed_time(e) for s, e in k1_events]
     del out
 

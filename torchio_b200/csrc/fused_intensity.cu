@@ -23,7 +23,7 @@ namespace tio {
 
 constexpr int A_TJ = 32;
 constexpr int A_TK = 64;
-constexpr int A_PLANES = 8;  // planes per CTA (amortises table setup)
+constexpr int A_PLANES = 16;  // planes per CTA (amortises table setup)
 
 struct BiasArgs {
   const float* coarse;  // [B][C][si][sj][sk] or null
@@ -217,6 +217,200 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
 #pragma unroll
         for (int o = 0; o < 8; ++o)
           if (j0 + jy + o < J) yp[(int64_t)(j0 + jy + o) * K] = acc[o];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------
+// pass 2, fast variant for table radius R <= 6 (sigma <= 2 voxels): fixed halo
+// (6 rows, 8 columns so that interior rows move as aligned float4), 13 zero-padded
+// taps held in registers, no per-tap branches.
+// -------------------------------------------------------------------------
+constexpr int F_R = 6;                    // taps = 13
+constexpr int F_HK = 8;                   // K halo, rounded up to keep 16-byte alignment
+constexpr int F_ROWS = A_TJ + 2 * F_R;    // 44
+constexpr int F_COLS = A_TK + 2 * F_HK;   // 80
+constexpr int F_PITCH = F_COLS + 4;       // 84 floats
+
+template <bool HAS_EPI>
+__device__ __forceinline__ void jk_epilogue4(float* v, const NoiseArgs& nz, const float* gamma,
+                                             bool noise_on, float mu, float sd, float gam,
+                                             int64_t flat0, int64_t stride, int valid) {
+  // v[0..3]: four outputs `stride` apart starting at flat index flat0; valid = how many exist
+  if (HAS_EPI && noise_on) {
+    float z1[4], z2[4];
+    if (nz.mode == 1) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (o < valid) {
+          z1[o] = __ldcs(nz.z + flat0 + o * stride);
+          if (nz.rician) z2[o] = __ldcs(nz.z2 + flat0 + o * stride);
+        }
+    } else {
+      const uint2 key = make_uint2((uint32_t)nz.philox_seed, (uint32_t)(nz.philox_seed >> 32));
+      const uint64_t gidx = (uint64_t)flat0;
+      uint4 rr = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0x6a6bu), key);
+      box_muller(rr.x, rr.y, z1[0], z1[1]);
+      box_muller(rr.z, rr.w, z1[2], z1[3]);
+      if (nz.rician) {
+        uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0x6a6bu), key);
+        box_muller(r2.x, r2.y, z2[0], z2[1]);
+        box_muller(r2.z, r2.w, z2[2], z2[3]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float n1 = __fadd_rn(mu, __fmul_rn(sd, z1[o]));
+      if (nz.rician) v[o] = rician(v[o], n1, __fadd_rn(mu, __fmul_rn(sd, z2[o])));
+      else v[o] = __fadd_rn(v[o], n1);
+    }
+  }
+  if (HAS_EPI && gamma) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) v[o] = signed_pow(v[o], gam);
+  }
+}
+
+template <bool HAS_EPI>
+__global__ void __launch_bounds__(256, 3)
+jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int I, int J,
+           int K, BlurArgs bl, NoiseArgs nz, const float* __restrict__ gamma) {
+  __shared__ __align__(16) float Abuf[2][F_ROWS * F_PITCH];  // input tile + halo, double buffered
+  __shared__ __align__(16) float Bm[F_ROWS * A_TK];          // after the K pass
+  __shared__ float taps_s[2][2 * F_R + 1];
+
+  const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
+  const int bc = blockIdx.z / tiles_i;
+  const int i_begin = (blockIdx.z % tiles_i) * A_PLANES;
+  const int i_end = min(i_begin + A_PLANES, I);
+  const int b = bc / C;
+  const int j0 = blockIdx.y * A_TJ, k0 = blockIdx.x * A_TK;
+  const int tid = threadIdx.x;
+  const int64_t n = (int64_t)I * J * K;
+  const float* x = src + (int64_t)bc * n;
+  float* y = dst + (int64_t)bc * n;
+
+  const int R = bl.R;
+  const int rj = bl.radius[1 * B + b], rk = bl.radius[2 * B + b];
+  const bool noise_on = HAS_EPI && nz.mode != 0 && (!nz.keep || nz.keep[b]);
+  const float mu = (HAS_EPI && nz.mode) ? nz.mean[b] : 0.0f, sd = (HAS_EPI && nz.mode) ? nz.std[b] : 0.0f;
+  const float gam = (HAS_EPI && gamma) ? gamma[b] : 1.0f;
+
+  if (tid < 2 * (2 * F_R + 1)) {  // 13 taps per axis, centred at index 6, zero beyond the radius
+    const int axis = tid < (2 * F_R + 1) ? 2 : 1;
+    const int s = tid < (2 * F_R + 1) ? tid : tid - (2 * F_R + 1);
+    const int off = s - F_R, rr = axis == 2 ? rk : rj;
+    float v = 0.0f;
+    if (rr > 0 && off >= -rr && off <= rr) v = bl.taps[((int64_t)axis * B + b) * (2 * R + 1) + R + off];
+    taps_s[axis == 2 ? 0 : 1][s] = v;
+  }
+  __syncthreads();
+  float tk[2 * F_R + 1], tj[2 * F_R + 1];
+#pragma unroll
+  for (int t = 0; t < 2 * F_R + 1; ++t) { tk[t] = taps_s[0][t]; tj[t] = taps_s[1][t]; }
+
+  const bool vec_rows = (k0 >= F_HK) && (k0 + A_TK + F_HK <= K) && ((K & 3) == 0) &&
+                        ((((uintptr_t)x) & 15) == 0);
+  const int row_lo = F_R - rj, row_hi = F_R + A_TJ + rj;  // rows the J pass will read
+
+  // stage plane i into buffer `buf`: [j0-6, j0+38) x [k0-8, k0+72), clamped = replicate
+  // padding.  Interior tiles stream with 16-byte cp.async (no register round trip).
+  auto stage = [&](int i, int buf) {
+    float* A = Abuf[buf];
+    const float* xp = x + (int64_t)i * J * K;
+    if (vec_rows) {
+      for (int idx = tid; idx < F_ROWS * (F_COLS / 4); idx += 256) {
+        const int r = idx / (F_COLS / 4), c4 = idx - r * (F_COLS / 4);
+        if (r < row_lo || r >= row_hi) continue;
+        const int jj = min(max(j0 - F_R + r, 0), J - 1);
+        const float* gp = xp + (int64_t)jj * K + (k0 - F_HK) + 4 * c4;
+        const uint32_t sp = (uint32_t)__cvta_generic_to_shared(A + r * F_PITCH + 4 * c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+      }
+    } else {
+      for (int idx = tid; idx < F_ROWS * F_COLS; idx += 256) {
+        const int r = idx / F_COLS, c = idx - r * F_COLS;
+        if (r < row_lo || r >= row_hi) continue;
+        const int jj = min(max(j0 - F_R + r, 0), J - 1);
+        const int kk = min(max(k0 - F_HK + c, 0), K - 1);
+        A[r * F_PITCH + c] = __ldg(xp + (int64_t)jj * K + kk);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(i_begin, 0);
+  for (int i = i_begin; i < i_end; ++i) {
+    const int cur = (i - i_begin) & 1;
+    if (i + 1 < i_end) {
+      stage(i + 1, cur ^ 1);  // prefetch the next plane while this one is convolved
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* A = Abuf[cur];
+    // ---- K pass: 16 threads x 4 outputs per row; window = cols k4+2 .. k4+17 ----
+    {
+      const int k4 = (tid & 15) * 4;
+      for (int r = tid >> 4; r < F_ROWS; r += 16) {
+        if (r < row_lo || r >= row_hi) continue;
+        float acc[4];
+        if (rk == 0) {
+          const float4 q = *(const float4*)(A + r * F_PITCH + F_HK + k4);
+          acc[0] = q.x; acc[1] = q.y; acc[2] = q.z; acc[3] = q.w;
+        } else {
+          float win[16];
+          const float2* wp = (const float2*)(A + r * F_PITCH + (F_HK - F_R) + k4);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) { const float2 q = wp[m]; win[2 * m] = q.x; win[2 * m + 1] = q.y; }
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = 0.0f;
+#pragma unroll
+          for (int s = 0; s < 2 * F_R + 1; ++s)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o] = __fmaf_rn(tk[s], win[o + s], acc[o]);
+        }
+        *(float4*)(Bm + r * A_TK + k4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+    __syncthreads();
+    // ---- J pass: thread = (k lane, 8 consecutive j), then epilogue + store ----
+    {
+      const int kx = tid & 63, jy = (tid >> 6) * 8;
+      const int k = k0 + kx;
+      float acc[8];
+      if (rj == 0) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = Bm[(F_R + jy + o) * A_TK + kx];
+      } else {
+        float win[8 + 2 * F_R];
+#pragma unroll
+        for (int w = 0; w < 8 + 2 * F_R; ++w) {
+          const int r = jy + w;  // rows outside [row_lo, row_hi) were not produced: their taps are 0
+          win[w] = (r >= row_lo && r < row_hi) ? Bm[r * A_TK + kx] : 0.0f;
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+#pragma unroll
+        for (int s = 0; s < 2 * F_R + 1; ++s)
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] = __fmaf_rn(tj[s], win[o + s], acc[o]);
+      }
+      if (k < K) {
+        const int64_t base = (int64_t)i * J * K + (int64_t)(j0 + jy) * K + k;
+        const int valid = min(8, J - (j0 + jy));
+        if (HAS_EPI) {
+          jk_epilogue4<HAS_EPI>(acc, nz, gamma, noise_on, mu, sd, gam, (int64_t)bc * n + base, K, valid);
+          jk_epilogue4<HAS_EPI>(acc + 4, nz, gamma, noise_on, mu, sd, gam,
+                                (int64_t)bc * n + base + 4 * (int64_t)K, K, valid - 4);
+        }
+        float* yp = y + base;
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (o < valid) yp[(int64_t)o * K] = acc[o];
       }
     }
     __syncthreads();
@@ -477,8 +671,14 @@ static int fused_impl(const float* src, float* dst, float* scratch, int B, int C
     // pass 2: K-conv, J-conv, then noise and gamma at the store
     const int64_t tiles = (int64_t)B * C * ((I + A_PLANES - 1) / A_PLANES);
     TIO_CHECK_ARG(tiles <= 65535, "%s: batch too large for the blur grid", who);
-    if (bl.R <= 6) launch_jk<6>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
-    else launch_jk<16>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
+    if (bl.R <= F_R) {
+      const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
+      dim3 grid((K + A_TK - 1) / A_TK, (J + A_TJ - 1) / A_TJ, B * C * tiles_i);
+      if (nz.mode != 0 || gamma) jk6_kernel<true><<<grid, 256, 0, st>>>(cur, dst, B, C, I, J, K, bl, nz, gamma);
+      else jk6_kernel<false><<<grid, 256, 0, st>>>(cur, dst, B, C, I, J, K, bl, nz, gamma);
+    } else {
+      launch_jk<16>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
+    }
   }
   TIO_CHECK_LAUNCH();
   return 0;
