@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: skip the nvidia-smi sampler")
     return ap.parse_args()
 
 
@@ -193,7 +194,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
     if sampler:
         sampler.start()
     torch.manual_seed(1234 + rank)

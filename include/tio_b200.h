@@ -80,8 +80,12 @@ int tio_abi_version(void);
  *              the pre-image of a 16^3 output tile).  The tile path applies to
  *              fp32 + TIO_LINEAR with K % 4 == 0; anything else, and any tile
  *              whose pre-image does not fit, uses the general kernel.
+ *   workspace  device scratch of tio_resample_workspace_bytes(B, OI, OJ, OK) bytes,
+ *              16-byte aligned (per-tile records of the TMA path); may be NULL,
+ *              which selects the general kernel.  The library allocates nothing.
  * src and dst must not alias.
  */
+size_t tio_resample_workspace_bytes(int B, int OI, int OJ, int OK);
 int tio_resample(const void* src, void* dst, int dtype,
                  int B, int C, int I, int J, int K,
                  int OI, int OJ, int OK,
@@ -89,7 +93,7 @@ int tio_resample(const void* src, void* dst, int dtype,
                  int ni, int nj, int nk,
                  const float* spacing_in, const float* spacing_out,
                  int affine_first, int mode, const float* fill, int box_hint,
-                 void* stream);
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Per-channel minimum of batch element 0 -> fill[C] on the device, no host
@@ -147,7 +151,7 @@ int tio_noise(const float* src, float* dst, int B, int64_t per_elem,
               const float* z, const float* z2, void* stream);
 
 /*
- * K4b — same, with normals generated in registers from Philox4x32-10 keyed by
+ * K4b — same, with normals generated in registers from Philox4x32-7 keyed by
  * (seed, global element index): statistically equivalent, NOT the reference
  * stream.  `rician` selects the two-draw variant.
  */
@@ -173,7 +177,7 @@ int tio_gamma(const float* src, float* dst, int B, int64_t per_elem,
  * Equal to running K2, K3, K4, K5 one after another up to fp32 summation order
  * (the separable passes commute; the reference order is I, J, K).
  *   noise_mode 1: normals supplied in z (z2 for the second Rician draw)
- *   noise_mode 2: Philox4x32-10 keyed by philox_seed (NOT the reference stream)
+ *   noise_mode 2: Philox4x32-7 keyed by philox_seed (NOT the reference stream)
  *   per-element identity rows (bias_identity[b], all radii 0, keep[b] == 0,
  *   gamma[b] == 1) pass through every stage as bit-exact copies
  *   scratch: B*C*I*J*K floats, required when axes_mask has bit 1 or 2 (J/K)

@@ -41,4 +41,4 @@ def test_bad_arguments_fail_loudly_without_touching_the_gpu():
         p = ctypes.addressof(buf)
         sp = (ctypes.c_float * 3)(1, 1, 1)
         _native.call("tio_resample", p, p, 0, 1, 1, 2, 2, 2, 2, 2, 2, p, None, None, 0, 0, 0,
-                     ctypes.addressof(sp), ctypes.addressof(sp), 1, 1, None, 0, None)
+                     ctypes.addressof(sp), ctypes.addressof(sp), 1, 1, None, 0, None, 0, None)

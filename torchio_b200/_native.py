@@ -9,7 +9,7 @@ missing or a call fails, a RuntimeError carrying ``tio_last_error()`` is raised.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libtio_b200.so"
@@ -19,7 +19,8 @@ _SIGNATURES = {
     "tio_abi_version": [],
     "tio_resample": [c_void_p, c_void_p, c_int] + [c_int] * 8
     + [c_void_p, c_void_p, c_void_p] + [c_int] * 3
-    + [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    + [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    "tio_resample_workspace_bytes": [c_int, c_int, c_int, c_int],
     "tio_min_sample0": [c_void_p, c_int, c_int64, c_void_p, c_void_p],
     "tio_bias_field": [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 3
     + [c_void_p, c_int, c_void_p],
@@ -53,7 +54,7 @@ def lib() -> ctypes.CDLL:
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
-            fn.restype = c_int
+            fn.restype = c_size_t if name.endswith("_bytes") else c_int
         _lib = handle
     return _lib
 

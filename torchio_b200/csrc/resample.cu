@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ src,
   }
 }
 
-int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st);
+int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st);
+size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK);
 
 }  // namespace tio
 
@@ -149,7 +151,7 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
                             const uint8_t* flags, int ni, int nj, int nk,
                             const float* spacing_in, const float* spacing_out,
                             int affine_first, int mode, const float* fill, int box_hint,
-                            void* stream) {
+                            void* workspace, size_t workspace_bytes, void* stream) {
   using namespace tio;
   TIO_CHECK_ARG(src && dst && mat, "tio_resample: null src/dst/mat");
   TIO_CHECK_ARG(src != dst, "tio_resample: src and dst must not alias");
@@ -179,7 +181,7 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   a.cp_in_smem = cp && ((size_t)ni * nj * nk * 12 <= 96 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TIO_F32 && mode == TIO_LINEAR && box_hint >= 0) {
-    const int rc = launch_resample_tile(a, box_hint, st);
+    const int rc = launch_resample_tile(a, box_hint, workspace, workspace_bytes, st);
     if (rc == 0) {
       TIO_CHECK_LAUNCH();
       return 0;
@@ -197,6 +199,10 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   }
   TIO_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" size_t tio_resample_workspace_bytes(int B, int OI, int OJ, int OK) {
+  return tio::resample_tile_workspace_bytes(B, OI, OJ, OK);
 }
 
 extern "C" int tio_min_sample0(const float* src, int C, int64_t n, float* fill, void* stream) {

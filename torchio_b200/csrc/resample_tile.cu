@@ -572,7 +572,13 @@ static void launch_box(const CUtensorMap& tm, const ResampleArgs& a, const TileA
 
 // Returns 0 when launched, 1 when the fast path does not apply (caller falls back),
 // >1 on error.
-int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
+size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK) {
+  const size_t tiles = (size_t)B * ((OI + XT - 1) / XT) * ((OJ + XT - 1) / XT) * ((OK + XT - 1) / XT);
+  return tiles * sizeof(int4);
+}
+
+int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
   if ((a.K & 3) || ((uintptr_t)a.src & 15)) return 1;   // TMA strides must be 16-byte multiples
   if ((int64_t)a.B * a.C > (1 << 30)) return 1;
   const size_t ncp = a.cp ? (size_t)a.ni * a.nj * a.nk * 3 : 0;
@@ -609,8 +615,9 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
 
   dim3 grid((a.OK + XT - 1) / XT, (a.OJ + XT - 1) / XT, (unsigned)(a.B * tiles_i));
   const int64_t n_tiles = (int64_t)grid.x * grid.y * grid.z;
-  int4* records = nullptr;  // stream-ordered scratch: no state survives the call
-  if (cudaMallocAsync((void**)&records, (size_t)n_tiles * sizeof(int4), st) != cudaSuccess) return 1;
+  // per-tile records live in caller-provided workspace: no allocation, no state kept
+  if (!workspace || workspace_bytes < (size_t)n_tiles * sizeof(int4) || ((uintptr_t)workspace & 15)) return 1;
+  int4* records = (int4*)workspace;
   const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
   if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, records);
   else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, records);
@@ -618,7 +625,6 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, cudaStream_t st) {
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, records, st);
   else launch_box<32>(tm, a, ta, grid, smem, fast, records, st);
-  cudaFreeAsync(records, st);
   return 0;
 }
 
