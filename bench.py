@@ -211,6 +211,7 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.steps):
         out = step(resident)
     t1.record()
+    host_issue_ms = (time.perf_counter() - wall_begin) * 1e3 / args.steps
     barrier()
     wall_end = time.perf_counter()
     ms = t0.elapsed_time(t1)
@@ -283,6 +284,7 @@ def run_b200(args, rank, world, local_rank):
             "includes": "host param sampling + table upload + all kernels of the step",
         },
         "gpu_launches": launches,
+        "host_issue_ms_per_step": host_issue_ms,
         "roofline": {
             "kernel": "resample_kernel (K1, %d launches in the timed region)" % len(k1_ms),
             "bound": "hbm",

@@ -30,7 +30,7 @@ _BATCH_META_KEYS = ("_batch_size", "_batched_keys", "_keep")
 class AffineMatrix:
     """4x4 voxel->world matrix (float64, host)."""
 
-    __slots__ = ("_m",)
+    __slots__ = ("_m", "_spacing")
 
     def __init__(self, matrix: Any = None) -> None:
         if matrix is None:
@@ -44,6 +44,7 @@ class AffineMatrix:
         if m.shape != (4, 4):
             raise ValueError(f"AffineMatrix must be 4x4, got {tuple(m.shape)}")
         self._m = m
+        self._spacing = None  # cached; treat the matrix as immutable after construction
 
     @classmethod
     def from_spacing(cls, spacing, *, origin=(0.0, 0.0, 0.0), direction=None):
@@ -63,8 +64,10 @@ class AffineMatrix:
 
     @property
     def spacing(self) -> tuple[float, float, float]:
-        sp = np.sqrt(np.sum(self._m[:3, :3] ** 2, axis=0))
-        return (float(sp[0]), float(sp[1]), float(sp[2]))
+        if self._spacing is None:
+            sp = np.sqrt(np.sum(self._m[:3, :3] ** 2, axis=0))
+            self._spacing = (float(sp[0]), float(sp[1]), float(sp[2]))
+        return self._spacing
 
     @property
     def origin(self) -> tuple[float, float, float]:

@@ -58,12 +58,17 @@ def spatial_tables(affine_matrices, control_points, batch_size: int, a_in: np.nd
         return None
     mat = np.empty((batch_size, 12), dtype=np.float32)
     flags = np.zeros(batch_size, dtype=np.uint8)
-    shared = {}
-    for b, world in enumerate(affine_matrices):
-        key = id(world)
-        if key not in shared:
-            shared[key] = voxel_matrix(a_in, a_out, world)
-        mat[b] = shared[key]
+    rows = [b for b, w in enumerate(affine_matrices) if w is not None]
+    if len(rows) < batch_size:
+        identity = voxel_matrix(a_in, a_out, None)
+        for b, w in enumerate(affine_matrices):
+            if w is None:
+                mat[b] = identity
+    if rows:
+        # stacked inv/matmul == per-element calls bit for bit (same LAPACK/BLAS kernels)
+        worlds = np.stack([np.asarray(affine_matrices[b], dtype=np.float64) for b in rows])
+        m = np.linalg.inv(a_in) @ np.linalg.inv(worlds) @ a_out
+        mat[rows] = m.astype(np.float32)[:, :3].reshape(len(rows), 12)
     cp = None
     grids = [None if c is None else np.asarray(c, dtype=np.float32) for c in control_points]
     shapes = {g.shape for g in grids if g is not None}

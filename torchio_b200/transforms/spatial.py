@@ -149,6 +149,40 @@ def build_forward_affine(scales, degrees, translation, center: str, shape, affin
     return t
 
 
+def build_forward_affines(scales, degrees, translation, center: str, shape, affine) -> np.ndarray:
+    """`build_forward_affine` for (n, 3) parameter arrays -> (n, 4, 4).  Stacked
+    `np.matmul` runs the same inner kernel per matrix, so the result is
+    bit-identical to the per-element version (tests/test_host_params.py)."""
+    scaling = np.array(scales, dtype=np.float64)
+    rotation = np.array(degrees, dtype=np.float64)
+    shift = np.array(translation, dtype=np.float64)
+    if shape[-1] == 1:
+        scaling[:, 2] = 1.0
+        rotation[:, :2] = 0.0
+        shift[:, 2] = 0.0
+    n = len(scaling)
+    r = np.radians(rotation)
+    cx, sx, cy, sy, cz, sz = (np.cos(r[:, 0]), np.sin(r[:, 0]), np.cos(r[:, 1]), np.sin(r[:, 1]),
+                              np.cos(r[:, 2]), np.sin(r[:, 2]))
+    z, o = np.zeros(n), np.ones(n)
+    row = lambda a, b, c: np.stack([a, b, c], axis=-1)  # noqa: E731
+    mx = np.stack([row(o, z, z), row(z, cx, -sx), row(z, sx, cx)], axis=-2)
+    my = np.stack([row(cy, z, sy), row(z, o, z), row(-sy, z, cy)], axis=-2)
+    mz = np.stack([row(cz, -sz, z), row(sz, cz, z), row(z, z, o)], axis=-2)
+    diag = np.zeros((n, 3, 3))
+    diag[:, 0, 0], diag[:, 1, 1], diag[:, 2, 2] = scaling[:, 0], scaling[:, 1], scaling[:, 2]
+    rs = (mz @ my @ mx) @ diag
+    t = np.zeros((n, 4, 4))
+    t[:, 3, 3] = 1.0
+    t[:, :3, :3] = rs
+    if center == "image":
+        m = affine.numpy()
+        c = m[:3, 3] + m[:3, :3] @ ((np.asarray(shape, dtype=np.float64) - 1) / 2)
+        t[:, :3, 3] = c - rs @ c
+    t[:, :3, 3] += shift
+    return t
+
+
 def _sample_control_points(grid_shape, max_displacement, locked_borders: int) -> Tensor:
     """U(-max, +max) per axis, outer shells zeroed (spatial.py:2241-2266)."""
     field = torch.rand(*grid_shape, 3, dtype=torch.float32)
@@ -406,10 +440,13 @@ class Spatial(SpatialTransform):
                 fields[:, border] = 0; fields[:, -1 - border] = 0
                 fields[:, :, border] = 0; fields[:, :, -1 - border] = 0
                 fields[:, :, :, border] = 0; fields[:, :, :, -1 - border] = 0
+        if has_affine.any():
+            rows = np.nonzero(has_affine)[0]
+            mats = build_forward_affines(scales[rows], degrees[rows], translation[rows],
+                                         self.center, shape, affine)
+            for row, mat in zip(rows, mats):
+                forwards[kept[row]] = mat
         for row, index in enumerate(kept):
-            if has_affine[row]:
-                forwards[index] = build_forward_affine(
-                    scales[row], degrees[row], translation[row], self.center, shape, affine)
             if elastic:
                 cps[index] = fields[row]
                 disps[index] = [float(v) for v in max_disp[row]]
@@ -596,13 +633,18 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
     if packed is None:  # exact no-op: data and affines untouched (spatial.py:579-590)
         return
     sp_out = np.asarray(a_out.spacing, dtype=np.float64)
-    for index, cp in enumerate(cps):
+    worst, grid_shape = None, None
+    for index, cp in enumerate(cps):  # one warning for the batch: test the largest displacement
         if cp is None:
             continue
         disp = max_displacements[index] if max_displacements else None
         if disp is None:
             disp = np.abs(cp).reshape(-1, 3).max(axis=0)
-        _check_folding(cp.shape[:3], disp, out_shape, sp_out)
+        disp = np.asarray(disp, dtype=np.float64)
+        worst = disp if worst is None else np.maximum(worst, disp)
+        grid_shape = cp.shape[:3]
+    if worst is not None:
+        _check_folding(grid_shape, worst, out_shape, sp_out)
     device = first.data.device
     mat_d, cp_d, flags_d = ops.upload(device, packed.mat, packed.cp, packed.flags)
     box_hint = _box_hint(packed, a_in.spacing, a_out.spacing, out_shape)
@@ -642,10 +684,11 @@ def _box_hint(packed, sp_in, sp_out, out_shape) -> int:
         cp = packed.cp
         spacing = np.minimum(np.asarray(sp_in, dtype=np.float64), np.asarray(sp_out))
         variation = np.zeros(3)
+        # adjacent control points differ by at most twice the largest magnitude
+        delta = 2.0 * np.abs(cp).reshape(-1, 3).max(axis=0)
         for axis in range(3):
             n_cp, n_out = cp.shape[1 + axis], out_shape[axis]
             if n_cp > 1 and n_out > 1:
-                delta = np.abs(np.diff(cp, axis=1 + axis)).reshape(-1, 3).max(axis=0)
                 variation += delta * ((n_cp - 1) / (n_out - 1)) * 15.0
         # all three partial derivatives peaking together is the rare case: budget a
         # third of the worst case, outlier tiles take the in-kernel fallback
