@@ -137,6 +137,26 @@ int tio_blur(const float* src, float* dst, float* scratch,
              const uint8_t* identity, void* stream);
 
 /*
+ * K4a — exact replay of torch's CPU `randn` stream on the device:
+ * mt19937(seed) -> 24-bit uniforms -> 16-wide Box-Muller blocks (ATen normal_fill;
+ * the stream the reference depends on through torch.randn(generator=CPU),
+ * noise.py:166-178).  Writes stream elements [offset, offset+n) to z[0..n).
+ * Requires offset % 16 == 0, n % 16 == 0, n >= 16 (ragged tails and tiny draws
+ * stay on the host), and offset + n <= 2^31 words.
+ *   table      device copy of the jump-ahead table built once by
+ *              tio_mt19937_build_table (host, ~2 s; depends only on MT19937, so
+ *              callers cache it; tio_mt19937_table_bytes() gives its size)
+ *   workspace  device scratch of tio_randn_mt19937_workspace_bytes(offset, n)
+ * Values agree with torch.randn to ~1 ulp (CUDA libm vs the host's log/sin/cos).
+ */
+size_t tio_mt19937_table_bytes(void);
+int tio_mt19937_build_table(void* host_blob, size_t bytes);
+size_t tio_randn_mt19937_workspace_bytes(uint64_t offset, uint64_t n);
+int tio_randn_mt19937(uint64_t seed, uint64_t offset, uint64_t n, float* z,
+                      const void* table, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/*
  * K4 — additive Gaussian / Rician noise.  Replaces _sample_noise + add +
  * _restore_gated_out (transforms/intensity/noise.py:98-178).
  *   dst = src + (mean[b] + std[b] * z)                       (Gaussian)

@@ -4,6 +4,7 @@ inputs, odd shapes, large rotations, coordinates far out of bounds,
 pass-through rows, multi-channel data, every label dtype."""
 
 import ctypes
+import json
 
 import numpy as np
 import pytest
@@ -290,3 +291,47 @@ def json_equal(h1, h2):
 
     f = lambda h: json.dumps([{"name": t.name, "params": t.params} for t in h], sort_keys=True)
     return f(h1) == f(h2)
+
+
+@pytest.mark.parametrize("seed,offset,n", [(0, 0, 16), (1234, 0, 4096), (7, 0, 3 * 2**20 + 1600),
+                                           (2**31 - 1, 16 * 12345, 2**20), (99, 40 * 2**20, 2**21 + 32)])
+def test_device_mt19937_randn_matches_torch_cpu_stream(seed, offset, n):
+    """K4a: the device replay equals torch.randn(generator=CPU(seed)) element for
+    element (to ~1 ulp of libm), at any 16-aligned stream position, across
+    segment (2^20) and coarse (2^25) jump boundaries."""
+    from torchio_b200 import ops
+
+    g = torch.Generator().manual_seed(seed)
+    if offset:
+        torch.randn(offset, generator=g)
+    want = torch.randn(n, generator=g)
+    got = ops.randn_mt19937(seed, offset, n, "cuda").cpu()
+    diff = (got - want).abs()
+    assert float(diff.max()) <= 2e-6, (float(diff.max()), int((diff > 2e-6).sum()))
+    assert float((got != want).float().mean()) < 0.2  # mostly bit-identical
+
+
+def test_noise_exact_mode_uses_device_stream_and_matches_reference():
+    """Noise in exact mode == the oracle (host torch.randn) for aligned and ragged
+    shapes, two images sharing one stream, and the second Rician draw."""
+    import copy
+    import warnings
+
+    import torchio_b200 as tio
+    from oracle import torch_port
+
+    for shape, rician in (((2, 1, 16, 16, 16), False), ((3, 1, 8, 16, 10), True), ((2, 1, 5, 7, 3), False)):
+        g = torch.Generator().manual_seed(3)
+        imgs = {"t1": torch.rand(shape, generator=g), "t2": torch.rand(shape, generator=g)}
+        batch = tio.SubjectsBatch({k: tio.ImagesBatch(v.clone().cuda(), [tio.AffineMatrix() for _ in range(shape[0])])
+                                   for k, v in imgs.items()})
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = tio.Noise(mean=(-0.1, 0.1), std=(0.05, 0.25), rician=rician)
+        torch.manual_seed(11)
+        out = t(batch)
+        params = out.applied_transforms[0].params
+        ref = {k: {"kind": "scalar", "data": v.clone(), "affines": [np.eye(4)] * shape[0]} for k, v in imgs.items()}
+        torch_port.noise(ref, json.loads(json.dumps(params)))
+        for k in imgs:
+            assert float((out.images[k].data.cpu() - ref[k]["data"]).abs().max()) <= 2e-6

@@ -30,6 +30,11 @@ _SIGNATURES = {
     "tio_noise_philox": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                          c_uint64, c_int, c_void_p],
     "tio_gamma": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p],
+    "tio_mt19937_table_bytes": [],
+    "tio_mt19937_build_table": [c_void_p, c_size_t],
+    "tio_randn_mt19937_workspace_bytes": [c_uint64, c_uint64],
+    "tio_randn_mt19937": [c_uint64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_size_t,
+                          c_void_p],
     "tio_intensity_fused": [c_void_p, c_void_p, c_void_p] + [c_int] * 5
     + [c_void_p, c_int, c_int, c_int, c_void_p, c_int]
     + [c_void_p, c_void_p, c_int, c_int]

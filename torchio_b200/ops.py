@@ -308,3 +308,63 @@ def intensity_fused(
         )
     _count(_fused_launches(axes_mask if taps is not None else 0, coarse is not None))
     return dst
+
+
+# ---- exact replay of torch's CPU randn stream (K4a) ---------------------------
+
+_MT_TABLE_FILE = _native.LIB_PATH.parent / "mt19937_jump.bin"
+_mt_host_table: Tensor | None = None
+_mt_device_tables: dict = {}
+_mt_lock = threading.Lock()
+MT_MAX_WORDS = 1 << 31  # stream positions the two-level jump table reaches
+
+
+def mt19937_host_table() -> Tensor:
+    """Jump-ahead table (constants of MT19937): loaded from the file written at
+    build time, else computed on the host (~2 s) and cached."""
+    global _mt_host_table
+    with _mt_lock:
+        if _mt_host_table is None:
+            lib = _native.lib()
+            nbytes = lib.tio_mt19937_table_bytes()
+            blob = None
+            if _MT_TABLE_FILE.exists() and _MT_TABLE_FILE.stat().st_size == nbytes:
+                blob = torch.from_numpy(np.fromfile(_MT_TABLE_FILE, dtype=np.uint8))
+            if blob is None:
+                blob = torch.zeros(nbytes, dtype=torch.uint8)
+                _native.call("tio_mt19937_build_table", blob.data_ptr(), nbytes)
+                try:
+                    blob.numpy().tofile(_MT_TABLE_FILE)
+                except OSError:
+                    pass
+            _mt_host_table = blob
+        return _mt_host_table
+
+
+def _mt_table(device: torch.device) -> Tensor:
+    key = (device.type, device.index)
+    table = _mt_device_tables.get(key)
+    if table is None:
+        table = mt19937_host_table().to(device)
+        _mt_device_tables[key] = table
+    return table
+
+
+def randn_mt19937(seed: int, offset: int, n: int, device, out: Tensor | None = None) -> Tensor:
+    """Elements [offset, offset+n) of ``torch.randn(N, generator=CPU mt19937(seed))``
+    computed on ``device`` (to ~1 ulp of the host's libm).  Needs offset, n
+    multiples of 16 and offset + n <= 2**31; callers keep ragged tails on the host."""
+    device = torch.device(device)
+    if n < 16 or n % 16 or offset % 16 or offset + n > MT_MAX_WORDS:
+        raise ValueError("randn_mt19937: offset and n must be multiples of 16, n >= 16,"
+                         " offset + n <= 2**31")
+    z = torch.empty(n, dtype=torch.float32, device=device) if out is None else out
+    lib = _native.lib()
+    ws_bytes = lib.tio_randn_mt19937_workspace_bytes(offset, n)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    table = _mt_table(device)
+    with torch.cuda.device(device):
+        _native.call("tio_randn_mt19937", int(seed) & 0xFFFFFFFF, offset, n, _ptr(z), _ptr(table),
+                     _ptr(workspace), ws_bytes, torch.cuda.current_stream(device).cuda_stream)
+    _count(4)
+    return z

@@ -159,10 +159,10 @@ def _blur_stage(ib, params):
 
 
 def _noise_mode() -> str:
-    """"exact": normals are torch.randn draws of the recorded CPU-generator seed
-    (the reference's stream; generated on the host and uploaded, as the
-    reference itself does on a GPU batch, noise.py:177).  "philox": in-kernel
-    counter-based normals — same distribution, different stream."""
+    """"exact" (default): the normals are the torch.randn draws of the recorded
+    CPU-generator seed — the reference's stream (noise.py:166-178) — replayed on
+    the device by `ops.randn_mt19937` (host torch.randn only for ragged shapes).
+    "philox": in-kernel counter-based normals — same distribution, other stream."""
     mode = os.environ.get("TIO_B200_NOISE", "exact").lower()
     if mode not in ("exact", "philox"):
         raise ValueError(f"TIO_B200_NOISE must be 'exact' or 'philox', got {mode!r}")
@@ -212,6 +212,37 @@ def _noise_stage_factory(params):
     rician = bool(params.get("rician", False))
     keep = params.get("_keep")
 
+    consumed = [0]  # words of the seed's stream used so far (across images and draws)
+
+    def draw(shape, device):
+        """Next ``prod(shape)`` normals of the stream: on the device when the
+        position allows (multiples of 16), else with torch.randn on the host,
+        which the generator object keeps aligned with ``consumed``."""
+        n = int(np.prod(shape))
+        start = consumed[0]
+        on_device = (not ragged[0] and n >= 16 and n % 16 == 0 and start % 16 == 0
+                     and start + n <= ops.MT_MAX_WORDS and device.type == "cuda")
+        if n < 16 or n % 16:
+            ragged[0] = True  # torch's tail/scalar paths: stay on the host from here on
+        consumed[0] = start + n + (16 if (n >= 16 and n % 16) else 0)
+        if on_device:
+            return ops.randn_mt19937(params["seed"], start, n, device).view(shape), None
+        # host path: fast-forward the CPU generator to `start` if the device path was used
+        if host_state[0] != start:
+            skip = start - host_state[0]
+            if skip % 16 == 0 and skip >= 16:
+                torch.randn(skip, generator=generator)
+            else:
+                raise RuntimeError("Noise: cannot realign the host generator (ragged stream)")
+        pin = torch.cuda.is_available()
+        z = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+        torch.randn(shape, generator=generator, out=z)
+        host_state[0] = consumed[0]
+        return None, z
+
+    host_state = [0]
+    ragged = [False]
+
     def stage(ib, index):
         shape = ib.data.shape
         b = shape[0]
@@ -225,15 +256,12 @@ def _noise_stage_factory(params):
             out["noise_mode"] = 2
             out["philox_seed"] = (int(params["seed"]) << 8) | (index & 0xFF)
             return out
-        pin = torch.cuda.is_available()
         out["noise_mode"] = 1
-        z = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
-        torch.randn(shape, generator=generator, out=z)
-        out["z_host"] = z
+        z_dev, z_host = draw(shape, ib.data.device)
+        out["z" if z_dev is not None else "z_host"] = z_dev if z_dev is not None else z_host
         if rician:
-            z2 = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
-            torch.randn(shape, generator=generator, out=z2)
-            out["z2_host"] = z2
+            z_dev, z_host = draw(shape, ib.data.device)
+            out["z2" if z_dev is not None else "z2_host"] = z_dev if z_dev is not None else z_host
         return out
 
     return stage
