@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--workload", default="full", choices=["full", "config2"])
     ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
     ap.add_argument("--size", type=int, default=VOL)
-    ap.add_argument("--noise", default=os.environ.get("TIO_B200_NOISE", "philox"),
+    ap.add_argument("--noise", default=os.environ.get("TIO_B200_NOISE", "exact"),
                     choices=["exact", "philox"])
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

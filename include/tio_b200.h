@@ -147,7 +147,8 @@ int tio_blur(const float* src, float* dst, float* scratch,
  *              tio_mt19937_build_table (host, ~2 s; depends only on MT19937, so
  *              callers cache it; tio_mt19937_table_bytes() gives its size)
  *   workspace  device scratch of tio_randn_mt19937_workspace_bytes(offset, n)
- * Values agree with torch.randn to ~1 ulp (CUDA libm vs the host's log/sin/cos).
+ * The uniforms are bit-identical to torch.s; normals agree to <= 4e-6 absolute
+ * (CUDA libm vs the host.s log/sin/cos).
  */
 size_t tio_mt19937_table_bytes(void);
 int tio_mt19937_build_table(void* host_blob, size_t bytes);
