@@ -311,12 +311,12 @@ jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
 #pragma unroll
   for (int t = 0; t < 2 * F_R + 1; ++t) { tk[t] = taps_s[0][t]; tj[t] = taps_s[1][t]; }
 
-  const bool vec_rows = (k0 >= F_HK) && (k0 + A_TK + F_HK <= K) && ((K & 3) == 0) &&
-                        ((((uintptr_t)x) & 15) == 0);
+  const bool vec_rows = ((K & 3) == 0) && ((((uintptr_t)x) & 15) == 0);
   const int row_lo = F_R - rj, row_hi = F_R + A_TJ + rj;  // rows the J pass will read
 
   // stage plane i into buffer `buf`: [j0-6, j0+38) x [k0-8, k0+72), clamped = replicate
-  // padding.  Interior tiles stream with 16-byte cp.async (no register round trip).
+  // padding.  16-byte chunks that lie inside the row stream with cp.async (no register
+  // round trip); the chunks hanging over the volume edge are filled element by element.
   auto stage = [&](int i, int buf) {
     float* A = Abuf[buf];
     const float* xp = x + (int64_t)i * J * K;
@@ -325,9 +325,16 @@ jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
         const int r = idx / (F_COLS / 4), c4 = idx - r * (F_COLS / 4);
         if (r < row_lo || r >= row_hi) continue;
         const int jj = min(max(j0 - F_R + r, 0), J - 1);
-        const float* gp = xp + (int64_t)jj * K + (k0 - F_HK) + 4 * c4;
-        const uint32_t sp = (uint32_t)__cvta_generic_to_shared(A + r * F_PITCH + 4 * c4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+        const int kk = k0 - F_HK + 4 * c4;
+        const float* row = xp + (int64_t)jj * K;
+        float* sp = A + r * F_PITCH + 4 * c4;
+        if (kk >= 0 && kk + 4 <= K) {
+          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sp);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(row + kk) : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sp[e] = __ldg(row + min(max(kk + e, 0), K - 1));
+        }
       }
     } else {
       for (int idx = tid; idx < F_ROWS * F_COLS; idx += 256) {
