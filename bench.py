@@ -327,7 +327,9 @@ def cpu_reference(args, steps, warmup):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    b = args.cpu_sample_batch
+    # bounded sample: ~13 s per step at batch 2 on the GPU box's 128 host threads; keep the
+    # whole --steps run within a few minutes by dropping to one volume for long runs
+    b = args.cpu_sample_batch if steps * args.cpu_sample_batch <= 24 else 1
     size = args.size
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
