@@ -75,7 +75,7 @@ int tio_abi_version(void);
  *              in-bounds weight sum, even for nearest data (:1722-1727).
  *   box_hint   host int selecting the kernel: < 0 = general gather kernel only
  *              (exact mul+add tap sum); 0 = TMA tile path with the default
- *              24^3 input box; 20 / 24 / 32 = TMA tile path with that box edge
+ *              24^3 input box; 20 / 22 / 24 / 28 / 32 = TMA tile path with that box edge
  *              (callers that know the matrices pick the smallest box covering
  *              the pre-image of a 16^3 output tile).  The tile path applies to
  *              fp32 + TIO_LINEAR with K % 4 == 0; anything else, and any tile

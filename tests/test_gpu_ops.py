@@ -87,7 +87,7 @@ def test_resample_bit_exact_vs_c_oracle(shape, mode, elastic):
             assert torch.equal(got, want), int((got != want).sum())
             if mode == 1:
                 # TMA tile path: same coordinates and fill decisions, FMA tap blending
-                for hint in (0, 20, 32):
+                for hint in (0, 20, 22, 28, 32):
                     fast, _ = _run_both(data, mat, cp, flags, (0.8, 1.1, 2.0), (0.8, 1.1, 2.0),
                                         affine_first, mode, fill, box_hint=hint)
                     assert float((fast - want).abs().max()) <= 1e-6

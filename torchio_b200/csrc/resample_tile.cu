@@ -355,7 +355,8 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const int i1 = min(i0 + XT, a.OI) - 1;
   // lanes 0-15 / 16-31 of a warp take rows DJ apart: with row pitch BK the two
   // half-warps then hit disjoint banks (DJ * BK == 16 mod 32) for axis-aligned reads
-  constexpr int DJ = (BOX == 20) ? 2 : 4;
+  // BK = 24, 26, 28, 32, 36 -> DJ = 2, 8, 4, (none: 4), 4
+  constexpr int DJ = (BOX == 20) ? 2 : (BOX == 22) ? 8 : 4;
   const int warp = tid >> 5, half = (tid >> 4) & 1;
   const int jrow = (warp % DJ) + (warp / DJ) * (2 * DJ) + half * DJ;
   const int oj = j0 + jrow, ok = k0 + (tid & 15);
@@ -585,7 +586,9 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
   if (ncp * 4 > 32 * 1024) return 1;
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return 1;
-  int box = box_hint <= 20 && box_hint > 0 ? 20 : (box_hint > 24 ? 32 : 24);
+  // supported box edges; 0 (auto) = 24
+  int box = 24;
+  if (box_hint > 0) box = box_hint <= 20 ? 20 : box_hint <= 22 ? 22 : box_hint <= 24 ? 24 : box_hint <= 28 ? 28 : 32;
   const int tiles_i = (a.OI + XT - 1) / XT;
   if ((int64_t)a.B * tiles_i > 65535 || (a.OJ + XT - 1) / XT > 65535) return 1;
 
@@ -623,7 +626,9 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
   else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, records);
   const size_t smem = ((size_t)box * box * (box + 4) + 64 + 4 + ncp) * sizeof(float);
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);
+  else if (box == 22) launch_box<22>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, records, st);
+  else if (box == 28) launch_box<28>(tm, a, ta, grid, smem, fast, records, st);
   else launch_box<32>(tm, a, ta, grid, smem, fast, records, st);
   return 0;
 }

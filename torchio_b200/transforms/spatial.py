@@ -673,7 +673,7 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
 
 
 def _box_hint(packed, sp_in, sp_out, out_shape) -> int:
-    """Edge (20/24/32) of the input box covering the pre-image of a 16^3 output
+    """Edge (20/22/24/28/32) of the input box covering the pre-image of a 16^3 output
     tile for every element: sum_b |M_ab| * 15 voxels + 2 taps, plus the largest
     change an elastic field can make across the tile (adjacent control-point
     deltas x control cells per voxel).  Tiles that still do not fit fall back to
@@ -694,9 +694,10 @@ def _box_hint(packed, sp_in, sp_out, out_shape) -> int:
         # third of the worst case, outlier tiles take the in-kernel fallback
         extent = extent + variation / spacing / 3.0
     worst = float(np.max(extent))
-    if worst <= 20.0:
-        return 20
-    return 24 if worst <= 24.0 else 32
+    for edge in (20, 22, 24, 28):
+        if worst <= edge:
+            return edge
+    return 32
 
 
 class Affine(Spatial):
