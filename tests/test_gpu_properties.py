@@ -115,15 +115,16 @@ def test_resample_block_matches_c_oracle_at_full_size():
     # near-identity affine so the pre-image of the block stays inside a known crop
     m = np.eye(4); m[:3, :3] += rng.uniform(-0.02, 0.02, (3, 3)); m[:3, 3] = rng.uniform(-1, 1, 3)
     mat = m.astype(np.float32)[:3].reshape(1, 12)
+    mat_t = torch.tensor(mat)  # kept alive: the oracle receives its raw pointer
     lab = _labels(1)
     for data, mode in ((x, 1), (lab, 0)):
-        got = ops.resample(data.cuda(), torch.tensor(mat).cuda(), None, None, (1, 1, 1), (1, 1, 1),
+        got = ops.resample(data.cuda(), mat_t.cuda(), None, None, (1, 1, 1), (1, 1, 1),
                            affine_first=True, mode=mode, fill=None, box_hint=-1).cpu()
         want = torch.empty_like(data)
         p = c_port._p
         sp = torch.ones(3)
         c_port.lib().orc_resample(p(data), p(want), c_port._DTYPES[data.dtype], 1, 1, S, S, S, S, S, S,
-                                  p(torch.tensor(mat)), None, None, 0, 0, 0, p(sp), p(sp), 1, mode, None)
+                                  p(mat_t), None, None, 0, 0, 0, p(sp), p(sp), 1, mode, None)
         assert torch.equal(got, want)
 
 
