@@ -452,7 +452,9 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
           "r"(smem_u32(bar))
           : "memory");
     }
-    {  // wait for the box (phase parity = c & 1)
+    // wait for the box (phase parity = c & 1): one warp polls the mbarrier, the other
+    // seven park on the hardware barrier instead of burning issue slots in a spin loop
+    if (tid < 32) {
       const uint32_t parity = (uint32_t)(c & 1);
       uint32_t done;
       do {
@@ -467,6 +469,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
             : "memory");
       } while (!done);
     }
+    __syncthreads();
     if (active) {
       float* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
       if (HAS_FILL && !tile_interior)
