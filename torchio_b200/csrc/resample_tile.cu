@@ -209,8 +209,67 @@ struct LiEntry {  // per output plane of the tile: I-axis lerp of the control gr
   float l0, l1;
 };
 
-// The 16-plane walk of one (j,k) column over the staged box.  CHECK = the tile
-// touches the volume border and a fill value is set: per-voxel ATen mask.
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2/FADD2/FMUL2) ---------------------------
+// Two IEEE fp32 lanes per 64-bit register, each rounded exactly like the scalar
+// instruction; a scalar operand packed with itself is encoded by ptxas as a broadcast
+// (no extra register).  The walk is issue-bound, so halving the FP instruction count
+// by treating two output planes at once is the lever (the FP32 pipe does the same work).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 bc(float x) { return pack2(x, x); }
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 add2_rd(f2 a, f2 b) {
+  f2 d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// affine_row (resample_common.cuh) on two positions at once
+__device__ __forceinline__ f2 affine_row2(const float* m, f2 pi, f2 pj, f2 pk) {
+  f2 acc = mul2(pi, bc(m[0]));
+  acc = fma2(pj, bc(m[1]), acc);
+  acc = fma2(pk, bc(m[2]), acc);
+  return add2(acc, bc(m[3]));  // fma(1, m3, acc) == rn(m3 + acc)
+}
+template <bool FASTDIV>
+__device__ __forceinline__ f2 norm_div2(f2 x, float hd, float rcp) {
+  if (FASTDIV) {
+    const f2 q0 = mul2(x, bc(rcp));
+    const f2 e = fma2(q0, bc(-hd), x);  // fma(-q0, hd, x): the sign moves to the exact operand
+    return fma2(e, bc(rcp), q0);
+  }
+  float lo, hi;
+  unpack2(x, lo, hi);
+  return pack2(__fdiv_rn(lo, hd), __fdiv_rn(hi, hd));
+}
+
+// The 16-plane walk of one (j,k) column over the staged box, two planes per step.
+// CHECK = the tile touches the volume border and a fill value is set: per-voxel ATen mask.
 template <int BOX, bool HAS_CP, bool CHECK, bool FASTDIV>
 __device__ __forceinline__ void walk_column(
     const ResampleArgs& a, const TileArgs& ta, const float* __restrict__ box,
@@ -234,26 +293,58 @@ __device__ __forceinline__ void walk_column(
   }
   int cur0 = -1, cur1 = -1;
   float r_lo[3] = {0.f, 0.f, 0.f}, r_hi[3] = {0.f, 0.f, 0.f};
-#pragma unroll 2
-  for (int oi = i0; oi <= i1; ++oi, out += ostride) {
+  // spacing divides of the displacement stay scalar (rare: non-unit spacing)
+  const bool unit_spacing = a.affine_first ? ta.sp_in_one : ta.sp_out_one;
+
+  auto refresh = [&](const LiEntry& li) {  // J/K-collapsed control values of the I-cell pair
+    if (li.off0 != cur0 || li.off1 != cur1) {
+      const float* p0 = cps + li.off0;
+      const float* p1 = cps + li.off1;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
+        float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
+        r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
+        float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
+        float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
+        r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
+      }
+      cur0 = li.off0; cur1 = li.off1;
+    }
+  };
+  // exact ATen mask for a voxel with out-of-bounds corners: ordered sum of the in-bounds weights
+  auto needs_fill = [&](int c0, int c1, int c2, float u0, float u1, float u2, float f0, float f1,
+                        float f2_, float hi0, float hi1, float hi2) -> bool {
+    const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
+                lo2 = __fsub_rn(__fadd_rn(f2_, 1.0f), u2);
+    const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
+    const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
+    const bool il = (unsigned)c0 < (unsigned)a.I, ih = (unsigned)(c0 + 1) < (unsigned)a.I;
+    const bool jl = (unsigned)c1 < (unsigned)a.J, jh = (unsigned)(c1 + 1) < (unsigned)a.J;
+    const bool kl = (unsigned)c2 < (unsigned)a.K, kh = (unsigned)(c2 + 1) < (unsigned)a.K;
+    float msum = 0.0f;
+    if (il & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w00, lo2));
+    if (ih & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w10, lo2));
+    if (il & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w01, lo2));
+    if (ih & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w11, lo2));
+    if (il & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w00, hi2));
+    if (ih & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w10, hi2));
+    if (il & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w01, hi2));
+    if (ih & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w11, hi2));
+    return !(msum > 0.5f);
+  };
+  auto interior = [&](int c0, int c1, int c2) -> bool {
+    return ((unsigned)c0 < (unsigned)(a.I - 1)) & ((unsigned)c1 < (unsigned)(a.J - 1)) &
+           ((unsigned)c2 < (unsigned)(a.K - 1));
+  };
+
+  // ---- one plane (odd tail, cell changes inside a pair, non-unit spacing) ----
+  auto one = [&](const int oi, float* __restrict__ dst) {
     const float pi = (float)oi;
     float q0, q1, q2;
     if (HAS_CP && elastic) {
       const LiEntry li = li_tab[oi - i0];  // warp-uniform broadcast
-      if (li.off0 != cur0 || li.off1 != cur1) {
-        const float* p0 = cps + li.off0;
-        const float* p1 = cps + li.off1;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
-          float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
-          r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
-          float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
-          float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
-          r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
-        }
-        cur0 = li.off0; cur1 = li.off1;
-      }
+      refresh(li);
       float d0 = lerp2(li.l0, r_lo[0], li.l1, r_hi[0]);
       float d1 = lerp2(li.l0, r_lo[1], li.l1, r_hi[1]);
       float d2 = lerp2(li.l0, r_lo[2], li.l1, r_hi[2]);
@@ -284,8 +375,8 @@ __device__ __forceinline__ void walk_column(
     const float u2 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q2, hd2, rc2), 1.0f), 1.0f), hs2);
     // floor via round-down magic add: the mantissa holds floor(u)
     const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
-    const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2 = __fsub_rn(s2, kMagic);
-    const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2);
+    const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2_ = __fsub_rn(s2, kMagic);
+    const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2_);
     const int b0 = __float_as_int(s0), b1 = __float_as_int(s1), b2 = __float_as_int(s2);
     // byte address of tap (floor i, floor j, floor k): one base register, the other
     // seven taps are compile-time immediates off it
@@ -293,27 +384,7 @@ __device__ __forceinline__ void walk_column(
     bool use_fill = false;
     if (CHECK) {
       const int c0 = b0 - kMagicBits, c1 = b1 - kMagicBits, c2 = b2 - kMagicBits;
-      const bool vox_interior = ((unsigned)c0 < (unsigned)(a.I - 1)) & ((unsigned)c1 < (unsigned)(a.J - 1)) &
-                                ((unsigned)c2 < (unsigned)(a.K - 1));
-      if (!vox_interior) {  // exact ATen mask: ordered sum of the in-bounds corner weights
-        const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
-                    lo2 = __fsub_rn(__fadd_rn(f2, 1.0f), u2);
-        const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
-        const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
-        const bool il = (unsigned)c0 < (unsigned)a.I, ih = (unsigned)(c0 + 1) < (unsigned)a.I;
-        const bool jl = (unsigned)c1 < (unsigned)a.J, jh = (unsigned)(c1 + 1) < (unsigned)a.J;
-        const bool kl = (unsigned)c2 < (unsigned)a.K, kh = (unsigned)(c2 + 1) < (unsigned)a.K;
-        float msum = 0.0f;
-        if (il & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w00, lo2));
-        if (ih & jl & kl) msum = __fadd_rn(msum, __fmul_rn(w10, lo2));
-        if (il & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w01, lo2));
-        if (ih & jh & kl) msum = __fadd_rn(msum, __fmul_rn(w11, lo2));
-        if (il & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w00, hi2));
-        if (ih & jl & kh) msum = __fadd_rn(msum, __fmul_rn(w10, hi2));
-        if (il & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w01, hi2));
-        if (ih & jh & kh) msum = __fadd_rn(msum, __fmul_rn(w11, hi2));
-        use_fill = !(msum > 0.5f);
-      }
+      if (!interior(c0, c1, c2)) use_fill = needs_fill(c0, c1, c2, u0, u1, u2, f0, f1, f2_, hi0, hi1, hi2);
     }
     // separable lerp K -> J -> I over the zero-padded box (<= 1 ulp from ATen's 8-term
     // weighted sum; the zero halo == skipping out-of-bounds corners)
@@ -329,8 +400,96 @@ __device__ __forceinline__ void walk_column(
     const float bb1 = __fmaf_rn(hi1, a11 - a10, a10);
     float v = __fmaf_rn(hi0, bb1 - bb0, bb0);
     if (CHECK && use_fill) v = fill_c;
-    *out = v;
+    *dst = v;
+  };
+
+  // ---- two planes (oi, oi+1) in packed registers: same operations, lane by lane ----
+  const f2 pj2 = bc(pj), pk2 = bc(pk);
+  int oi = i0;
+  f2 pi2 = pack2((float)i0, (float)(i0 + 1));
+#pragma unroll 1
+  for (; oi + 1 <= i1; oi += 2, out += 2 * ostride, pi2 = add2(pi2, bc(2.0f))) {
+    f2 q0, q1, q2;
+    if (HAS_CP && elastic) {
+      const LiEntry la = li_tab[oi - i0], lb = li_tab[oi + 1 - i0];
+      if (!unit_spacing || la.off0 != lb.off0 || la.off1 != lb.off1) {
+        one(oi, out);
+        one(oi + 1, out + ostride);
+        continue;
+      }
+      refresh(la);
+      const f2 l0 = pack2(la.l0, lb.l0), l1 = pack2(la.l1, lb.l1);
+      const f2 d0 = fma2(l0, bc(r_lo[0]), mul2(l1, bc(r_hi[0])));
+      const f2 d1 = fma2(l0, bc(r_lo[1]), mul2(l1, bc(r_hi[1])));
+      const f2 d2 = fma2(l0, bc(r_lo[2]), mul2(l1, bc(r_hi[2])));
+      if (a.affine_first) {
+        if (identity) {
+          q0 = add2(pi2, d0); q1 = add2(pj2, d1); q2 = add2(pk2, d2);
+        } else {
+          q0 = add2(affine_row2(m + 0, pi2, pj2, pk2), d0);
+          q1 = add2(affine_row2(m + 4, pi2, pj2, pk2), d1);
+          q2 = add2(affine_row2(m + 8, pi2, pj2, pk2), d2);
+        }
+      } else {
+        const f2 e0 = add2(pi2, d0), e1 = add2(pj2, d1), e2 = add2(pk2, d2);
+        q0 = affine_row2(m + 0, e0, e1, e2);
+        q1 = affine_row2(m + 4, e0, e1, e2);
+        q2 = affine_row2(m + 8, e0, e1, e2);
+      }
+    } else {
+      q0 = affine_row2(m + 0, pi2, pj2, pk2);
+      q1 = affine_row2(m + 4, pi2, pj2, pk2);
+      q2 = affine_row2(m + 8, pi2, pj2, pk2);
+    }
+    const f2 one2 = bc(1.0f), mone2 = bc(-1.0f), magic2 = bc(kMagic), mmagic2 = bc(-kMagic);
+    const f2 u0 = mul2(add2(add2(norm_div2<FASTDIV>(q0, hd0, rc0), mone2), one2), bc(hs0));
+    const f2 u1 = mul2(add2(add2(norm_div2<FASTDIV>(q1, hd1, rc1), mone2), one2), bc(hs1));
+    const f2 u2 = mul2(add2(add2(norm_div2<FASTDIV>(q2, hd2, rc2), mone2), one2), bc(hs2));
+    const f2 s0 = add2_rd(u0, magic2), s1 = add2_rd(u1, magic2), s2 = add2_rd(u2, magic2);
+    const f2 f0 = add2(s0, mmagic2), f1 = add2(s1, mmagic2), f2_ = add2(s2, mmagic2);
+    const f2 hi0 = sub2(u0, f0), hi1 = sub2(u1, f1), hi2 = sub2(u2, f2_);
+    float s0a, s0b, s1a, s1b, s2a, s2b;
+    unpack2(s0, s0a, s0b); unpack2(s1, s1a, s1b); unpack2(s2, s2a, s2b);
+    const int b0a = __float_as_int(s0a), b1a = __float_as_int(s1a), b2a = __float_as_int(s2a);
+    const int b0b = __float_as_int(s0b), b1b = __float_as_int(s1b), b2b = __float_as_int(s2b);
+    const uint32_t addr_a = kbase + (((unsigned)b0a * C1 + (unsigned)b1a * C2 + (unsigned)b2a) << 2);
+    const uint32_t addr_b = kbase + (((unsigned)b0b * C1 + (unsigned)b1b * C2 + (unsigned)b2b) << 2);
+    bool fill_a = false, fill_b = false;
+    if (CHECK) {
+      const int c0a = b0a - kMagicBits, c1a = b1a - kMagicBits, c2a = b2a - kMagicBits;
+      const int c0b = b0b - kMagicBits, c1b = b1b - kMagicBits, c2b = b2b - kMagicBits;
+      const bool in_a = interior(c0a, c1a, c2a), in_b = interior(c0b, c1b, c2b);
+      if (!(in_a & in_b)) {
+        float ua[3], ub[3], fa[3], fb[3], ha[3], hb[3];
+        unpack2(u0, ua[0], ub[0]); unpack2(u1, ua[1], ub[1]); unpack2(u2, ua[2], ub[2]);
+        unpack2(f0, fa[0], fb[0]); unpack2(f1, fa[1], fb[1]); unpack2(f2_, fa[2], fb[2]);
+        unpack2(hi0, ha[0], hb[0]); unpack2(hi1, ha[1], hb[1]); unpack2(hi2, ha[2], hb[2]);
+        if (!in_a) fill_a = needs_fill(c0a, c1a, c2a, ua[0], ua[1], ua[2], fa[0], fa[1], fa[2], ha[0], ha[1], ha[2]);
+        if (!in_b) fill_b = needs_fill(c0b, c1b, c2b, ub[0], ub[1], ub[2], fb[0], fb[1], fb[2], hb[0], hb[1], hb[2]);
+      }
+    }
+    const f2 v000 = pack2(lds_f32<0>(addr_a), lds_f32<0>(addr_b));
+    const f2 v001 = pack2(lds_f32<4>(addr_a), lds_f32<4>(addr_b));
+    const f2 v010 = pack2(lds_f32<4 * C2>(addr_a), lds_f32<4 * C2>(addr_b));
+    const f2 v011 = pack2(lds_f32<4 * C2 + 4>(addr_a), lds_f32<4 * C2 + 4>(addr_b));
+    const f2 v100 = pack2(lds_f32<4 * C1>(addr_a), lds_f32<4 * C1>(addr_b));
+    const f2 v101 = pack2(lds_f32<4 * C1 + 4>(addr_a), lds_f32<4 * C1 + 4>(addr_b));
+    const f2 v110 = pack2(lds_f32<4 * (C1 + C2)>(addr_a), lds_f32<4 * (C1 + C2)>(addr_b));
+    const f2 v111 = pack2(lds_f32<4 * (C1 + C2) + 4>(addr_a), lds_f32<4 * (C1 + C2) + 4>(addr_b));
+    const f2 a00 = fma2(hi2, sub2(v001, v000), v000);
+    const f2 a01 = fma2(hi2, sub2(v011, v010), v010);
+    const f2 a10 = fma2(hi2, sub2(v101, v100), v100);
+    const f2 a11 = fma2(hi2, sub2(v111, v110), v110);
+    const f2 bb0 = fma2(hi1, sub2(a01, a00), a00);
+    const f2 bb1 = fma2(hi1, sub2(a11, a10), a10);
+    float va, vb;
+    unpack2(fma2(hi0, sub2(bb1, bb0), bb0), va, vb);
+    if (CHECK && fill_a) va = fill_c;
+    if (CHECK && fill_b) vb = fill_c;
+    out[0] = va;
+    out[ostride] = vb;
   }
+  if (oi <= i1) one(oi, out);
 }
 
 template <int BOX, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
