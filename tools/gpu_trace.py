@@ -22,7 +22,7 @@ for _ in range(4):
     step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for _ in range(4):
+    for _ in range(int(os.environ.get("TRACE_STEPS", "4"))):
         out = step()
     torch.cuda.synchronize()
 os.makedirs("gpurun_out", exist_ok=True)
@@ -32,6 +32,17 @@ gpu = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") a
 gpu.sort(key=lambda e: e["ts"])
 t0 = gpu[0]["ts"]
 prev_end = None
+busy = sum(e["dur"] for e in gpu)
+span = gpu[-1]["ts"] + gpu[-1]["dur"] - t0
+gaps = []
+pe = None
+for e in gpu:
+    if pe is not None and e["ts"] - pe > 100:
+        gaps.append(((e["ts"] - t0) / 1e3, (e["ts"] - pe) / 1e3, e["name"][:40]))
+    pe = e["ts"] + e["dur"]
+print(f"span {span/1e3:.2f} ms  busy {busy/1e3:.2f} ms  idle {(span-busy)/1e3:.2f} ms; gaps > 0.1 ms: {gaps}")
+if os.environ.get("TRACE_SUMMARY"):
+    sys.exit(0)
 for e in gpu:
     gap = 0 if prev_end is None else e["ts"] - prev_end
     name = e["name"][:60]

@@ -18,6 +18,7 @@
 // I, J, K; this runs I, K, J): differences are ~1e-7 relative.
 #include "common.cuh"
 #include "intensity_common.cuh"
+#include "tma.cuh"
 
 namespace tio {
 
@@ -224,62 +225,86 @@ jk_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, 
 }
 
 // -------------------------------------------------------------------------
-// pass 2, fast variant for table radius R <= 6 (sigma <= 2 voxels): fixed halo
-// (6 rows, 8 columns so that interior rows move as aligned float4), 13 zero-padded
-// taps held in registers, no per-tap branches.
+// pass 2, fast variant for table radius R <= 6 (sigma <= 2 voxels).
+//   staging   one TMA box per plane: [j0-6, j0+38) x [k0-8, k0+72) (80 floats = 320 B
+//             per row, 16-byte aligned origin), zero-filled outside the volume, two
+//             buffers so plane i+1 is in flight while plane i is convolved; a single
+//             thread issues it, so staging costs no issue slots.
+//   padding   replicate padding is applied where the data is consumed: the K pass
+//             reads the clamped source row (rows beyond the J border are the edge
+//             row, and conv_K commutes with that); on K-border tiles each half-warp
+//             first copies the edge column into its row's zero-filled halo.
+//   K pass    (row, 4 consecutive k): five aligned LDS.128 -> 13 taps x 4 outputs.
+//   J pass    (k, 8 consecutive j) from the K-pass plane (double buffered: one
+//             __syncthreads per plane), normals prefetched before the FMAs,
+//             noise (+Rician) and gamma at the store.
+// Taps are zero-padded to 13 and held in registers; no per-tap branches.
 // -------------------------------------------------------------------------
 constexpr int F_R = 6;                    // taps = 13
 constexpr int F_HK = 8;                   // K halo, rounded up to keep 16-byte alignment
 constexpr int F_ROWS = A_TJ + 2 * F_R;    // 44
-constexpr int F_COLS = A_TK + 2 * F_HK;   // 80
-constexpr int F_PITCH = F_COLS + 4;       // 84 floats
+constexpr int F_COLS = A_TK + 2 * F_HK;   // 80 (dense: the TMA box pitch)
+constexpr int F_ABUF = F_ROWS * F_COLS;   // floats per staged plane
+constexpr int F_BBUF = F_ROWS * A_TK;     // floats per K-pass plane
+constexpr size_t F_SMEM = (size_t)(2 * F_ABUF + 2 * F_BBUF + 32) * sizeof(float) + 2 * sizeof(uint64_t);
 
-template <bool HAS_EPI>
-__device__ __forceinline__ void jk_epilogue4(float* v, const NoiseArgs& nz, const float* gamma,
-                                             bool noise_on, float mu, float sd, float gam,
-                                             int64_t flat0, int64_t stride, int valid) {
-  // v[0..3]: four outputs `stride` apart starting at flat index flat0; valid = how many exist
-  if (HAS_EPI && noise_on) {
-    float z1[4], z2[4];
-    if (nz.mode == 1) {
+// K conv of 4 consecutive outputs (columns 8+k4 .. 8+k4+3 of a staged row), radius RK:
+// aligned 16-byte loads cover columns k4+4..k4+15 (RK <= 4) or k4..k4+19.
+template <int RK>
+__device__ __forceinline__ float4 kconv4(const float* __restrict__ row, const int k4, const float* tk) {
+  if (RK == 0) return *(const float4*)(row + F_HK + k4);
+  constexpr int M0 = RK <= 4 ? 1 : 0, M1 = RK <= 4 ? 4 : 5;
+  float win[20];
 #pragma unroll
-      for (int o = 0; o < 4; ++o)
-        if (o < valid) {
-          z1[o] = __ldcs(nz.z + flat0 + o * stride);
-          if (nz.rician) z2[o] = __ldcs(nz.z2 + flat0 + o * stride);
-        }
-    } else {
-      const uint2 key = make_uint2((uint32_t)nz.philox_seed, (uint32_t)(nz.philox_seed >> 32));
-      const uint64_t gidx = (uint64_t)flat0;
-      uint4 rr = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0x6a6bu), key);
-      box_muller(rr.x, rr.y, z1[0], z1[1]);
-      box_muller(rr.z, rr.w, z1[2], z1[3]);
-      if (nz.rician) {
-        uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0x6a6bu), key);
-        box_muller(r2.x, r2.y, z2[0], z2[1]);
-        box_muller(r2.z, r2.w, z2[2], z2[3]);
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const float n1 = __fadd_rn(mu, __fmul_rn(sd, z1[o]));
-      if (nz.rician) v[o] = rician(v[o], n1, __fadd_rn(mu, __fmul_rn(sd, z2[o])));
-      else v[o] = __fadd_rn(v[o], n1);
-    }
+  for (int m = M0; m < M1; ++m) {
+    const float4 q = *(const float4*)(row + k4 + 4 * m);
+    win[4 * m] = q.x; win[4 * m + 1] = q.y; win[4 * m + 2] = q.z; win[4 * m + 3] = q.w;
   }
-  if (HAS_EPI && gamma) {
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int o = 0; o < 4; ++o) v[o] = signed_pow(v[o], gam);
+  for (int t = -RK; t <= RK; ++t)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = __fmaf_rn(tk[F_R + t], win[F_HK + o + t], acc[o]);
+  return make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// J conv of 8 consecutive rows (F_R+jy .. F_R+jy+7 of the K-pass plane) at column kx
+template <int RJ>
+__device__ __forceinline__ void jconv8(const float* __restrict__ Bw, const int jy, const int kx,
+                                       const float* tj, float* acc) {
+  float win[8 + 2 * RJ];
+#pragma unroll
+  for (int w = 0; w < 8 + 2 * RJ; ++w) win[w] = Bw[(F_R - RJ + jy + w) * A_TK + kx];
+  if (RJ == 0) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = win[o];
+    return;
   }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+#pragma unroll
+  for (int t = -RJ; t <= RJ; ++t)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = __fmaf_rn(tj[F_R + t], win[o + t + RJ], acc[o]);
+}
+
+// sign(x) * |x|^g for g > 0 on the SFU: lg2(0) = -inf -> ex2 = 0, so zero needs no select
+__device__ __forceinline__ float signed_pow_pos(float x, float g) {
+  float l, p;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fabsf(x)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(__fmul_rn(g, l)));
+  return copysignf(p, x);
 }
 
 template <bool HAS_EPI>
 __global__ void __launch_bounds__(256, 3)
-jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int I, int J,
-           int K, BlurArgs bl, NoiseArgs nz, const float* __restrict__ gamma) {
-  __shared__ __align__(16) float Abuf[2][F_ROWS * F_PITCH];  // input tile + halo, double buffered
-  __shared__ __align__(16) float Bm[F_ROWS * A_TK];          // after the K pass
-  __shared__ float taps_s[2][2 * F_R + 1];
+jk6_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, int B, int C, int I,
+           int J, int K, BlurArgs bl, NoiseArgs nz, const float* __restrict__ gamma) {
+  extern __shared__ __align__(128) float smem[];
+  float* Abuf = smem;                    // [2][F_ROWS][F_COLS]  staged planes
+  float* Bbuf = smem + 2 * F_ABUF;       // [2][F_ROWS][A_TK]    after the K pass
+  float* taps_s = Bbuf + 2 * F_BBUF;     // [2][13] (+ padding)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(taps_s + 32);
 
   const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
   const int bc = blockIdx.z / tiles_i;
@@ -289,14 +314,27 @@ jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
   const int j0 = blockIdx.y * A_TJ, k0 = blockIdx.x * A_TK;
   const int tid = threadIdx.x;
   const int64_t n = (int64_t)I * J * K;
-  const float* x = src + (int64_t)bc * n;
-  float* y = dst + (int64_t)bc * n;
+
+  auto issue = [&](int i, int s) {  // one thread
+    const uint32_t bar = smem_u32(bars + s);
+    mbar_expect_tx(bar, (uint32_t)(F_ABUF * sizeof(float)));
+    tma_load_3d(smem_u32(Abuf + s * F_ABUF), &tmap, k0 - F_HK, j0 - F_R, bc * I + i, bar);
+  };
+  if (tid == 0) {
+    mbar_init(smem_u32(bars + 0), 1);
+    mbar_init(smem_u32(bars + 1), 1);
+    mbar_fence_init();
+    issue(i_begin, 0);
+  }
 
   const int R = bl.R;
   const int rj = bl.radius[1 * B + b], rk = bl.radius[2 * B + b];
   const bool noise_on = HAS_EPI && nz.mode != 0 && (!nz.keep || nz.keep[b]);
   const float mu = (HAS_EPI && nz.mode) ? nz.mean[b] : 0.0f, sd = (HAS_EPI && nz.mode) ? nz.std[b] : 0.0f;
   const float gam = (HAS_EPI && gamma) ? gamma[b] : 1.0f;
+  // gamma == 1 (gated rows) passes values through exactly; gamma <= 0 or NaN never comes
+  // from exp(log_gamma) but keeps the general helper
+  const int gamma_mode = !(HAS_EPI && gamma) || gam == 1.0f ? 0 : (gam > 0.0f ? 1 : 2);
 
   if (tid < 2 * (2 * F_R + 1)) {  // 13 taps per axis, centred at index 6, zero beyond the radius
     const int axis = tid < (2 * F_R + 1) ? 2 : 1;
@@ -304,123 +342,131 @@ jk6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
     const int off = s - F_R, rr = axis == 2 ? rk : rj;
     float v = 0.0f;
     if (rr > 0 && off >= -rr && off <= rr) v = bl.taps[((int64_t)axis * B + b) * (2 * R + 1) + R + off];
-    taps_s[axis == 2 ? 0 : 1][s] = v;
+    taps_s[(axis == 2 ? 0 : 13) + s] = v;
   }
   __syncthreads();
   float tk[2 * F_R + 1], tj[2 * F_R + 1];
 #pragma unroll
-  for (int t = 0; t < 2 * F_R + 1; ++t) { tk[t] = taps_s[0][t]; tj[t] = taps_s[1][t]; }
+  for (int t = 0; t < 2 * F_R + 1; ++t) { tk[t] = taps_s[t]; tj[t] = taps_s[13 + t]; }
 
-  const bool vec_rows = ((K & 3) == 0) && ((((uintptr_t)x) & 15) == 0);
-  const int row_lo = F_R - rj, row_hi = F_R + A_TJ + rj;  // rows the J pass will read
+  const int row_lo = F_R - rj, row_hi = F_R + A_TJ + rj;        // rows the J pass reads
+  const int rsrc_lo = max(0, F_R - j0), rsrc_hi = min(F_ROWS - 1, J - 1 - j0 + F_R);  // rows inside the volume
+  const int clo = max(0, F_HK - k0), chi = min(F_COLS - 1, K - 1 - k0 + F_HK);        // columns inside the volume
+  const bool kfix = (clo > F_HK - rk) || (chi < F_HK + A_TK + rk - 1);                // CTA-uniform
 
-  // stage plane i into buffer `buf`: [j0-6, j0+38) x [k0-8, k0+72), clamped = replicate
-  // padding.  16-byte chunks that lie inside the row stream with cp.async (no register
-  // round trip); the chunks hanging over the volume edge are filled element by element.
-  auto stage = [&](int i, int buf) {
-    float* A = Abuf[buf];
-    const float* xp = x + (int64_t)i * J * K;
-    if (vec_rows) {
-      for (int idx = tid; idx < F_ROWS * (F_COLS / 4); idx += 256) {
-        const int r = idx / (F_COLS / 4), c4 = idx - r * (F_COLS / 4);
-        if (r < row_lo || r >= row_hi) continue;
-        const int jj = min(max(j0 - F_R + r, 0), J - 1);
-        const int kk = k0 - F_HK + 4 * c4;
-        const float* row = xp + (int64_t)jj * K;
-        float* sp = A + r * F_PITCH + 4 * c4;
-        if (kk >= 0 && kk + 4 <= K) {
-          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sp);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(row + kk) : "memory");
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sp[e] = __ldg(row + min(max(kk + e, 0), K - 1));
-        }
-      }
-    } else {
-      for (int idx = tid; idx < F_ROWS * F_COLS; idx += 256) {
-        const int r = idx / F_COLS, c = idx - r * F_COLS;
-        if (r < row_lo || r >= row_hi) continue;
-        const int jj = min(max(j0 - F_R + r, 0), J - 1);
-        const int kk = min(max(k0 - F_HK + c, 0), K - 1);
-        A[r * F_PITCH + c] = __ldg(xp + (int64_t)jj * K + kk);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+  const int k4 = (tid & 15) * 4;
+  const int kx = tid & 63, jy = (tid >> 6) * 8;
+  const int k = k0 + kx;
+  const int valid = (k < K) ? min(8, J - (j0 + jy)) : 0;
+  const int plane_off = (j0 + jy) * K + k;  // within one plane (J*K < 2^31)
 
-  stage(i_begin, 0);
   for (int i = i_begin; i < i_end; ++i) {
-    const int cur = (i - i_begin) & 1;
-    if (i + 1 < i_end) {
-      stage(i + 1, cur ^ 1);  // prefetch the next plane while this one is convolved
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int it = i - i_begin, s = it & 1;
+    if (tid == 0 && i + 1 < i_end) issue(i + 1, s ^ 1);  // its last readers passed the previous barrier
+    mbar_wait(smem_u32(bars + s), (uint32_t)((it >> 1) & 1));
+    float* A = Abuf + s * F_ABUF;
+    float* Bw = Bbuf + s * F_BBUF;
+    // ---- K pass ----
+#pragma unroll 1
+    for (int r = row_lo + (tid >> 4); r < row_hi; r += 16) {
+      float* row = A + min(max(r, rsrc_lo), rsrc_hi) * F_COLS;
+      if (kfix) {
+        // replicate the edge column into the zero-filled halo of this half-warp's row.
+        // Other warps may patch the same (clamped) row with the same values; every
+        // reader has written them itself first, so any interleaving reads the same data.
+        const int c_lo = (F_HK - F_R) + (tid & 15);
+        if (c_lo < clo) row[c_lo] = row[clo];
+#pragma unroll 1
+        for (int c = chi + 1 + (tid & 15); c < F_HK + A_TK + F_R; c += 16) row[c] = row[chi];
+        __syncwarp();
+      }
+      float4 o4;
+      switch (rk) {
+        case 0: o4 = kconv4<0>(row, k4, tk); break;
+        case 1: o4 = kconv4<1>(row, k4, tk); break;
+        case 2: o4 = kconv4<2>(row, k4, tk); break;
+        case 3: o4 = kconv4<3>(row, k4, tk); break;
+        case 4: o4 = kconv4<4>(row, k4, tk); break;
+        case 5: o4 = kconv4<5>(row, k4, tk); break;
+        default: o4 = kconv4<6>(row, k4, tk); break;
+      }
+      *(float4*)(Bw + r * A_TK + k4) = o4;
     }
-    __syncthreads();
-    const float* A = Abuf[cur];
-    // ---- K pass: 16 threads x 4 outputs per row; window = cols k4+2 .. k4+17 ----
-    {
-      const int k4 = (tid & 15) * 4;
-      for (int r = tid >> 4; r < F_ROWS; r += 16) {
-        if (r < row_lo || r >= row_hi) continue;
-        float acc[4];
-        if (rk == 0) {
-          const float4 q = *(const float4*)(A + r * F_PITCH + F_HK + k4);
-          acc[0] = q.x; acc[1] = q.y; acc[2] = q.z; acc[3] = q.w;
-        } else {
-          float win[16];
-          const float2* wp = (const float2*)(A + r * F_PITCH + (F_HK - F_R) + k4);
+    // normals for this thread's 8 outputs: in flight across the barrier and the J pass
+    float z1[8], z2[8];
+    const int64_t flat0 = (int64_t)bc * n + (int64_t)i * J * K + plane_off;
+    if (HAS_EPI && noise_on && nz.mode == 1) {
+      const float* zp = nz.z + flat0;
+      if (valid == 8) {
 #pragma unroll
-          for (int m = 0; m < 8; ++m) { const float2 q = wp[m]; win[2 * m] = q.x; win[2 * m + 1] = q.y; }
+        for (int o = 0; o < 8; ++o, zp += K) z1[o] = __ldcs(zp);
+      } else {
 #pragma unroll
-          for (int o = 0; o < 4; ++o) acc[o] = 0.0f;
+        for (int o = 0; o < 8; ++o, zp += K)
+          if (o < valid) z1[o] = __ldcs(zp);
+      }
+      if (nz.rician) {
+        const float* zq = nz.z2 + flat0;
 #pragma unroll
-          for (int s = 0; s < 2 * F_R + 1; ++s)
-#pragma unroll
-            for (int o = 0; o < 4; ++o) acc[o] = __fmaf_rn(tk[s], win[o + s], acc[o]);
-        }
-        *(float4*)(Bm + r * A_TK + k4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        for (int o = 0; o < 8; ++o, zq += K)
+          if (o < valid) z2[o] = __ldcs(zq);
       }
     }
     __syncthreads();
     // ---- J pass: thread = (k lane, 8 consecutive j), then epilogue + store ----
-    {
-      const int kx = tid & 63, jy = (tid >> 6) * 8;
-      const int k = k0 + kx;
-      float acc[8];
-      if (rj == 0) {
+    float acc[8];
+    switch (rj) {
+      case 0: jconv8<0>(Bw, jy, kx, tj, acc); break;
+      case 1: jconv8<1>(Bw, jy, kx, tj, acc); break;
+      case 2: jconv8<2>(Bw, jy, kx, tj, acc); break;
+      case 3: jconv8<3>(Bw, jy, kx, tj, acc); break;
+      case 4: jconv8<4>(Bw, jy, kx, tj, acc); break;
+      case 5: jconv8<5>(Bw, jy, kx, tj, acc); break;
+      default: jconv8<6>(Bw, jy, kx, tj, acc); break;
+    }
+    if (valid > 0) {
+      if (HAS_EPI && noise_on) {
+        if (nz.mode == 2) {
+          const uint2 key = make_uint2((uint32_t)nz.philox_seed, (uint32_t)(nz.philox_seed >> 32));
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = Bm[(F_R + jy + o) * A_TK + kx];
-      } else {
-        float win[8 + 2 * F_R];
-#pragma unroll
-        for (int w = 0; w < 8 + 2 * F_R; ++w) {
-          const int r = jy + w;  // rows outside [row_lo, row_hi) were not produced: their taps are 0
-          win[w] = (r >= row_lo && r < row_hi) ? Bm[r * A_TK + kx] : 0.0f;
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t gidx = (uint64_t)(flat0 + (int64_t)(4 * h) * K);
+            uint4 rr = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0x6a6bu), key);
+            box_muller(rr.x, rr.y, z1[4 * h], z1[4 * h + 1]);
+            box_muller(rr.z, rr.w, z1[4 * h + 2], z1[4 * h + 3]);
+            if (nz.rician) {
+              uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0x6a6bu), key);
+              box_muller(r2.x, r2.y, z2[4 * h], z2[4 * h + 1]);
+              box_muller(r2.z, r2.w, z2[4 * h + 2], z2[4 * h + 3]);
+            }
+          }
         }
+        if (nz.rician) {
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+          for (int o = 0; o < 8; ++o)
+            acc[o] = rician(acc[o], __fadd_rn(mu, __fmul_rn(sd, z1[o])), __fadd_rn(mu, __fmul_rn(sd, z2[o])));
+        } else {
 #pragma unroll
-        for (int s = 0; s < 2 * F_R + 1; ++s)
-#pragma unroll
-          for (int o = 0; o < 8; ++o) acc[o] = __fmaf_rn(tj[s], win[o + s], acc[o]);
+          for (int o = 0; o < 8; ++o) acc[o] = __fadd_rn(acc[o], __fadd_rn(mu, __fmul_rn(sd, z1[o])));
+        }
       }
-      if (k < K) {
-        const int64_t base = (int64_t)i * J * K + (int64_t)(j0 + jy) * K + k;
-        const int valid = min(8, J - (j0 + jy));
-        if (HAS_EPI) {
-          jk_epilogue4<HAS_EPI>(acc, nz, gamma, noise_on, mu, sd, gam, (int64_t)bc * n + base, K, valid);
-          jk_epilogue4<HAS_EPI>(acc + 4, nz, gamma, noise_on, mu, sd, gam,
-                                (int64_t)bc * n + base + 4 * (int64_t)K, K, valid - 4);
-        }
-        float* yp = y + base;
+      if (gamma_mode == 1) {
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
-          if (o < valid) yp[(int64_t)o * K] = acc[o];
+        for (int o = 0; o < 8; ++o) acc[o] = signed_pow_pos(acc[o], gam);
+      } else if (gamma_mode == 2) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = signed_pow(acc[o], gam);
+      }
+      float* yp = dst + flat0;
+      if (valid == 8) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o, yp += K) *yp = acc[o];
+      } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o, yp += K)
+          if (o < valid) *yp = acc[o];
       }
     }
-    __syncthreads();
   }
 }
 
@@ -599,6 +645,182 @@ march_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int 
   }
 }
 
+// -------------------------------------------------------------------------
+// pass 1, fast variant for table radius R <= 6 and 16-byte aligned rows: the ring of
+// the last 13 planes lives in registers.  The plane loop is unrolled by 13 so every
+// ring slot is a fixed register: per voxel 13 FMAs, no shared-memory traffic, no
+// modular indexing.  Taps are zero-padded to 13 (smaller radii use the same code).
+//   EPI = this is the only pass (no J/K blur): noise and gamma at the store.
+// -------------------------------------------------------------------------
+template <bool HAS_BIAS, bool EPI>
+__global__ void __launch_bounds__(256, EPI ? 1 : 2)
+march6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int I, int J,
+              int K, BlurArgs bl, BiasArgs bi, NoiseArgs nz, const float* __restrict__ gamma) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int W = 2 * F_R + 1;
+  const int bc = blockIdx.z;
+  const int b = bc / C;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int64_t n = (int64_t)I * J * K;
+  const float* x = src + (int64_t)bc * n;
+  float* y = dst + (int64_t)bc * n;
+
+  const int r = bl.taps ? bl.radius[0 * B + b] : 0;
+  float* tapi = smem;      // [13] zero-padded, centred at 6
+  float* g = smem + 16;    // coarse bias grid
+  const int ns = HAS_BIAS ? bi.si * bi.sj * bi.sk : 0;
+  const bool bias_on = HAS_BIAS && !(bi.identity && bi.identity[b]);
+  if (tid < W) {
+    const int off = tid - F_R;
+    tapi[tid] = (r > 0 && off >= -r && off <= r) ? bl.taps[((int64_t)0 * B + b) * (2 * bl.R + 1) + bl.R + off] : 0.0f;
+  }
+  if (bias_on) {
+    const float* gs = bi.coarse + (int64_t)bc * ns;
+    for (int t = tid; t < ns; t += 256) g[t] = gs[t];
+  }
+  __syncthreads();
+  if (k >= K || j >= J) return;
+
+  const bool noise_on = EPI && nz.mode != 0 && (!nz.keep || nz.keep[b]);
+  const float mu = (EPI && nz.mode) ? nz.mean[b] : 0.0f, sd = (EPI && nz.mode) ? nz.std[b] : 0.0f;
+  const float gam = (EPI && gamma) ? gamma[b] : 1.0f;
+  const int gamma_mode = !(EPI && gamma) || gam == 1.0f ? 0 : (gam > 0.0f ? 1 : 2);
+
+  LerpAxis lj, lk[4];
+  int o00[4], o01[4], o10[4], o11[4];
+  int cur0 = -1, cur1 = -1;
+  float r_lo[4], r_hi[4];
+  if (bias_on) {
+    lj = lerp_axis(bi.sc_j, bi.sj, j);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      lk[v] = lerp_axis(bi.sc_k, bi.sk, k + v);
+      o00[v] = lj.i0 * bi.sk + lk[v].i0; o01[v] = lj.i0 * bi.sk + lk[v].i1;
+      o10[v] = lj.i1 * bi.sk + lk[v].i0; o11[v] = lj.i1 * bi.sk + lk[v].i1;
+    }
+  }
+  const int col = j * K + k;  // within one plane
+  const int plane = J * K;
+
+  auto load_plane = [&](int i, float* out) {
+    const float4 t = *(const float4*)(x + (int64_t)i * plane + col);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+    if (bias_on) {
+      const LerpAxis li = lerp_axis(bi.sc_i, bi.si, i);
+      if (li.i0 != cur0 || li.i1 != cur1) {
+        const float* p0 = g + (li.i0 * bi.sj) * bi.sk;
+        const float* p1 = g + (li.i1 * bi.sj) * bi.sk;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float a0 = lerp2(lk[v].l0, p0[o00[v]], lk[v].l1, p0[o01[v]]);
+          const float a1 = lerp2(lk[v].l0, p0[o10[v]], lk[v].l1, p0[o11[v]]);
+          r_lo[v] = lerp2(lj.l0, a0, lj.l1, a1);
+          const float b0 = lerp2(lk[v].l0, p1[o00[v]], lk[v].l1, p1[o01[v]]);
+          const float b1 = lerp2(lk[v].l0, p1[o10[v]], lk[v].l1, p1[o11[v]]);
+          r_hi[v] = lerp2(lj.l0, b0, lj.l1, b1);
+        }
+        cur0 = li.i0; cur1 = li.i1;
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float f = expf(lerp2(li.l0, r_lo[v], li.l1, r_hi[v]));
+        out[v] = bi.divide ? __fdiv_rn(out[v], f) : __fmul_rn(out[v], f);
+      }
+    }
+  };
+
+  auto finish = [&](int i, float* v) {
+    const int64_t o = (int64_t)i * plane + col;
+    if (EPI) {
+      if (noise_on) {
+        const int64_t flat = (int64_t)bc * n + o;
+        float z1[4], z2[4];
+        if (nz.mode == 1) {
+          const float4 t = __ldcs((const float4*)(nz.z + flat));
+          z1[0] = t.x; z1[1] = t.y; z1[2] = t.z; z1[3] = t.w;
+          if (nz.rician) {
+            const float4 u = __ldcs((const float4*)(nz.z2 + flat));
+            z2[0] = u.x; z2[1] = u.y; z2[2] = u.z; z2[3] = u.w;
+          }
+        } else {
+          const uint2 key = make_uint2((uint32_t)nz.philox_seed, (uint32_t)(nz.philox_seed >> 32));
+          const uint64_t gidx = (uint64_t)(flat / 4);
+          uint4 rr = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0x5eedu), key);
+          box_muller(rr.x, rr.y, z1[0], z1[1]);
+          box_muller(rr.z, rr.w, z1[2], z1[3]);
+          if (nz.rician) {
+            uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0x5eedu), key);
+            box_muller(r2.x, r2.y, z2[0], z2[1]);
+            box_muller(r2.z, r2.w, z2[2], z2[3]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float n1 = __fadd_rn(mu, __fmul_rn(sd, z1[q]));
+          if (nz.rician) v[q] = rician(v[q], n1, __fadd_rn(mu, __fmul_rn(sd, z2[q])));
+          else v[q] = __fadd_rn(v[q], n1);
+        }
+      }
+      if (gamma_mode == 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = signed_pow_pos(v[q], gam);
+      } else if (gamma_mode == 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = signed_pow(v[q], gam);
+      }
+    }
+    *(float4*)(y + o) = make_float4(v[0], v[1], v[2], v[3]);
+  };
+
+  if (r == 0) {  // no I-axis blur for this element: pure streaming
+    for (int i = 0; i < I; ++i) {
+      float v[4];
+      load_plane(i, v);
+      finish(i, v);
+    }
+    return;
+  }
+
+  float tp[W];
+#pragma unroll
+  for (int t = 0; t < W; ++t) tp[t] = tapi[t];
+  float ring[W][4];
+  {
+    float first[4];
+    load_plane(0, first);  // replicate padding below plane 0
+#pragma unroll
+    for (int sl = 0; sl < W; ++sl)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ring[sl][q] = first[q];
+  }
+  // position p enters slot p mod 13; output o = p - 6 reads positions p-12 .. p
+  for (int base = 0; base < I + F_R; base += W) {
+#pragma unroll
+    for (int ph = 0; ph < W; ++ph) {
+      const int p = base + ph;
+      if (p >= I + F_R) break;
+      if (p > 0 && p < I) load_plane(p, ring[ph]);
+      else if (p >= I) {  // replicate padding above plane I-1: the previous slot holds it
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ring[ph][q] = ring[(ph + W - 1) % W][q];
+      }
+      const int o = p - F_R;
+      if (o >= 0) {
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+          const int sl = (ph + 1 + t) % W;  // position p - 12 + t
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = __fmaf_rn(tp[t], ring[sl][q], acc[q]);
+        }
+        finish(o, acc);
+      }
+    }
+  }
+}
+
 static inline bool aligned16f(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 static float up_scale(int n_in, int n_out) {
@@ -669,7 +891,20 @@ static int fused_impl(const float* src, float* dst, float* scratch, int B, int C
                            (int)smem);                                                        \
     march_kernel<VV, BB><<<grid, block, smem, st>>>(cur, out, B, C, I, J, K, ib, bi, nz1, gamma1); \
   } while (0)
-    if (vec) { if (bi.coarse) TIO_LAUNCH_MARCH(4, true); else TIO_LAUNCH_MARCH(4, false); }
+    if (vec && R <= F_R) {
+      const size_t smem6 = (size_t)(16 + (ns + 3) / 4 * 4) * sizeof(float);
+#define TIO_LAUNCH_MARCH6(BB, EE)                                                              \
+  do {                                                                                         \
+    if (smem6 > 48 * 1024)                                                                     \
+      cudaFuncSetAttribute(march6_kernel<BB, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem6);                                                        \
+    march6_kernel<BB, EE><<<grid, block, smem6, st>>>(cur, out, B, C, I, J, K, ib, bi, nz1, gamma1); \
+  } while (0)
+      const bool epi = nz1.mode != 0 || gamma1 != nullptr;
+      if (bi.coarse) { if (epi) TIO_LAUNCH_MARCH6(true, true); else TIO_LAUNCH_MARCH6(true, false); }
+      else { if (epi) TIO_LAUNCH_MARCH6(false, true); else TIO_LAUNCH_MARCH6(false, false); }
+#undef TIO_LAUNCH_MARCH6
+    } else if (vec) { if (bi.coarse) TIO_LAUNCH_MARCH(4, true); else TIO_LAUNCH_MARCH(4, false); }
     else { if (bi.coarse) TIO_LAUNCH_MARCH(1, true); else TIO_LAUNCH_MARCH(1, false); }
 #undef TIO_LAUNCH_MARCH
     cur = out;
@@ -678,11 +913,32 @@ static int fused_impl(const float* src, float* dst, float* scratch, int B, int C
     // pass 2: K-conv, J-conv, then noise and gamma at the store
     const int64_t tiles = (int64_t)B * C * ((I + A_PLANES - 1) / A_PLANES);
     TIO_CHECK_ARG(tiles <= 65535, "%s: batch too large for the blur grid", who);
-    if (bl.R <= F_R) {
+    // TMA: 16-byte aligned base and row pitch; coordinates must fit int32
+    const bool tma_ok = bl.R <= F_R && (K % 4 == 0) && aligned16f(cur) && (int64_t)B * C * I < (1ll << 31);
+    EncodeTiledFn encode = tma_ok ? encode_tiled_fn() : nullptr;
+    CUtensorMap tm;
+    bool have_map = false;
+    if (encode) {
+      const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)J, (cuuint64_t)B * C * I};
+      const cuuint64_t gstride[2] = {(cuuint64_t)K * 4, (cuuint64_t)J * K * 4};
+      const cuuint32_t bdim[3] = {(cuuint32_t)F_COLS, (cuuint32_t)F_ROWS, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      have_map = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(cur), gdim, gstride,
+                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (have_map) {
       const int tiles_i = (I + A_PLANES - 1) / A_PLANES;
       dim3 grid((K + A_TK - 1) / A_TK, (J + A_TJ - 1) / A_TJ, B * C * tiles_i);
-      if (nz.mode != 0 || gamma) jk6_kernel<true><<<grid, 256, 0, st>>>(cur, dst, B, C, I, J, K, bl, nz, gamma);
-      else jk6_kernel<false><<<grid, 256, 0, st>>>(cur, dst, B, C, I, J, K, bl, nz, gamma);
+      if (nz.mode != 0 || gamma) {
+        cudaFuncSetAttribute(jk6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+        jk6_kernel<true><<<grid, 256, F_SMEM, st>>>(tm, dst, B, C, I, J, K, bl, nz, gamma);
+      } else {
+        cudaFuncSetAttribute(jk6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+        jk6_kernel<false><<<grid, 256, F_SMEM, st>>>(tm, dst, B, C, I, J, K, bl, nz, gamma);
+      }
+    } else if (bl.R <= F_R) {
+      launch_jk<6>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
     } else {
       launch_jk<16>(cur, dst, B, C, I, J, K, bl, nz, gamma, st);
     }

@@ -24,6 +24,7 @@
 #include <mutex>
 
 #include "resample_common.cuh"
+#include "tma.cuh"
 
 namespace tio {
 
@@ -37,10 +38,6 @@ struct TileArgs {
   float hs[3];   // (size-1)/2           (ATen un-normalise multiplier, exact)
   int sp_in_one, sp_out_one;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
 
 template <int OFFSET>
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -688,23 +685,6 @@ static bool fastdiv_admitted(float d, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_fd_mutex);
   g_fd_cache[key] = ok;
   return ok;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
 }
 
 template <int BOX, bool HAS_CP, bool FASTDIV>

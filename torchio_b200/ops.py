@@ -120,11 +120,15 @@ def upload(device: torch.device, *arrays):
         stage = stage[:offset]
     else:
         stage = torch.empty(offset, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    # plain memcpy through numpy views: torch's CPU copy_ fans tensors above 32 KiB out to
+    # the intra-op thread pool, and waking 100+ OpenMP threads on a busy host was measured
+    # to stall this call for tens of milliseconds (tools/host_stalls3.py)
+    stage_np = stage.numpy()
     for s in specs:
         if s is None:
             continue
         t, off, nbytes = s
-        stage[off:off + nbytes] = t.reshape(-1).view(torch.uint8)
+        stage_np[off:off + nbytes] = t.reshape(-1).numpy().view(np.uint8)
     dev = stage.to(device, non_blocking=True)
     if slot is not None:
         _ring.release(slot, torch.device(device))
