@@ -205,6 +205,13 @@ struct LiEntry {  // per output plane of the tile: I-axis lerp of the control gr
   int off0, off1;  // i0 * plane, i1 * plane (floats)
   float l0, l1;
 };
+struct __align__(16) LiPair {  // planes (2p, 2p+1) of the tile, weights laid out as fp32x2 operands
+  int off0, off1;    // of plane 2p
+  float l0a, l0b;    // l0 of plane 2p, 2p+1
+  float l1a, l1b;
+  int same_cell;     // both planes lerp between the same two control planes
+  int pad;
+};
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2/FADD2/FMUL2) ---------------------------
 // Two IEEE fp32 lanes per 64-bit register, each rounded exactly like the scalar
@@ -267,10 +274,15 @@ __device__ __forceinline__ f2 norm_div2(f2 x, float hd, float rcp) {
 
 // The 16-plane walk of one (j,k) column over the staged box, two planes per step.
 // CHECK = the tile touches the volume border and a fill value is set: per-voxel ATen mask.
-template <int BOX, bool HAS_CP, bool CHECK, bool FASTDIV>
+// EMODE (CTA-uniform, resolved outside the loop):
+//   0 no displacement            1 q = p + d (identity matrix, unit spacing)
+//   2 q = M p + d (unit spacing) 3 q = M (p + d) (unit spacing)
+//   4 displacement with non-unit spacing: plane-at-a-time path only
+template <int BOX, bool HAS_CP, bool CHECK, bool FASTDIV, int EMODE>
 __device__ __forceinline__ void walk_column(
     const ResampleArgs& a, const TileArgs& ta, const float* __restrict__ box,
-    const float* __restrict__ cps, const LiEntry* __restrict__ li_tab, const float m[12],
+    const float* __restrict__ cps, const LiEntry* __restrict__ li_tab,
+    const LiPair* __restrict__ li_pairs, const float m[12],
     const bool elastic, const bool identity, const uint32_t kbase, const int i0, const int i1,
     const int oj, const int ok, const float fill_c, float* __restrict__ out, const int64_t ostride) {
   constexpr int BK = BOX + 4;
@@ -290,20 +302,20 @@ __device__ __forceinline__ void walk_column(
   }
   int cur0 = -1, cur1 = -1;
   float r_lo[3] = {0.f, 0.f, 0.f}, r_hi[3] = {0.f, 0.f, 0.f};
-  // spacing divides of the displacement stay scalar (rare: non-unit spacing)
-  const bool unit_spacing = a.affine_first ? ta.sp_in_one : ta.sp_out_one;
 
   auto refresh = [&](const LiEntry& li) {  // J/K-collapsed control values of the I-cell pair
     if (li.off0 != cur0 || li.off1 != cur1) {
+      // control points straight from global memory: a tile touches at most 2x2 (j,k)
+      // cells, so these are a few L1-resident sectors per warp, once or twice per walk
       const float* p0 = cps + li.off0;
       const float* p1 = cps + li.off1;
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) {
-        float a00 = lerp2(lk.l0, p0[o00 + ax], lk.l1, p0[o01 + ax]);
-        float a01 = lerp2(lk.l0, p0[o10 + ax], lk.l1, p0[o11 + ax]);
+        float a00 = lerp2(lk.l0, __ldg(p0 + o00 + ax), lk.l1, __ldg(p0 + o01 + ax));
+        float a01 = lerp2(lk.l0, __ldg(p0 + o10 + ax), lk.l1, __ldg(p0 + o11 + ax));
         r_lo[ax] = lerp2(lj.l0, a00, lj.l1, a01);
-        float b00 = lerp2(lk.l0, p1[o00 + ax], lk.l1, p1[o01 + ax]);
-        float b01 = lerp2(lk.l0, p1[o10 + ax], lk.l1, p1[o11 + ax]);
+        float b00 = lerp2(lk.l0, __ldg(p1 + o00 + ax), lk.l1, __ldg(p1 + o01 + ax));
+        float b01 = lerp2(lk.l0, __ldg(p1 + o10 + ax), lk.l1, __ldg(p1 + o11 + ax));
         r_hi[ax] = lerp2(lj.l0, b00, lj.l1, b01);
       }
       cur0 = li.off0; cur1 = li.off1;
@@ -405,28 +417,34 @@ __device__ __forceinline__ void walk_column(
   int oi = i0;
   f2 pi2 = pack2((float)i0, (float)(i0 + 1));
 #pragma unroll 1
-  for (; oi + 1 <= i1; oi += 2, out += 2 * ostride, pi2 = add2(pi2, bc(2.0f))) {
+  for (; oi <= i1; oi += 2, out += 2 * ostride, pi2 = add2(pi2, bc(2.0f))) {
     f2 q0, q1, q2;
-    if (HAS_CP && elastic) {
-      const LiEntry la = li_tab[oi - i0], lb = li_tab[oi + 1 - i0];
-      if (!unit_spacing || la.off0 != lb.off0 || la.off1 != lb.off1) {
-        one(oi, out);
-        one(oi + 1, out + ostride);
-        continue;
-      }
-      refresh(la);
-      const f2 l0 = pack2(la.l0, lb.l0), l1 = pack2(la.l1, lb.l1);
+    // planes go one at a time (single call site, the scalar body is large) when the pair
+    // straddles a control cell, at the odd tail, and for EMODE 4 (spacing divides)
+    bool pair_ok = (EMODE != 4) && (oi + 1 <= i1);
+    LiPair lp;
+    if (EMODE != 0 && EMODE != 4) {
+      lp = li_pairs[(oi - i0) >> 1];  // warp-uniform broadcast (two LDS.128)
+      pair_ok = pair_ok && lp.same_cell;
+    }
+    if (!pair_ok) {
+      const int last = min(oi + 1, i1);
+#pragma unroll 1
+      for (int t = oi; t <= last; ++t) one(t, out + (t - oi) * ostride);
+      continue;
+    }
+    if (EMODE != 0) {
+      refresh(LiEntry{lp.off0, lp.off1, lp.l0a, lp.l1a});
+      const f2 l0 = pack2(lp.l0a, lp.l0b), l1 = pack2(lp.l1a, lp.l1b);
       const f2 d0 = fma2(l0, bc(r_lo[0]), mul2(l1, bc(r_hi[0])));
       const f2 d1 = fma2(l0, bc(r_lo[1]), mul2(l1, bc(r_hi[1])));
       const f2 d2 = fma2(l0, bc(r_lo[2]), mul2(l1, bc(r_hi[2])));
-      if (a.affine_first) {
-        if (identity) {
-          q0 = add2(pi2, d0); q1 = add2(pj2, d1); q2 = add2(pk2, d2);
-        } else {
-          q0 = add2(affine_row2(m + 0, pi2, pj2, pk2), d0);
-          q1 = add2(affine_row2(m + 4, pi2, pj2, pk2), d1);
-          q2 = add2(affine_row2(m + 8, pi2, pj2, pk2), d2);
-        }
+      if (EMODE == 1) {
+        q0 = add2(pi2, d0); q1 = add2(pj2, d1); q2 = add2(pk2, d2);
+      } else if (EMODE == 2) {
+        q0 = add2(affine_row2(m + 0, pi2, pj2, pk2), d0);
+        q1 = add2(affine_row2(m + 4, pi2, pj2, pk2), d1);
+        q2 = add2(affine_row2(m + 8, pi2, pj2, pk2), d2);
       } else {
         const f2 e0 = add2(pi2, d0), e1 = add2(pj2, d1), e2 = add2(pk2, d2);
         q0 = affine_row2(m + 0, e0, e1, e2);
@@ -486,11 +504,10 @@ __device__ __forceinline__ void walk_column(
     out[0] = va;
     out[ostride] = vb;
   }
-  if (oi <= i1) one(oi, out);
 }
 
 template <int BOX, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArgs a,
                      const TileArgs ta, const int4* __restrict__ records) {
   constexpr int BK = BOX + 4;  // inner (K) box extent: room for the 16-byte origin alignment
@@ -498,14 +515,15 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   // layout: [box floats | li table (16 entries) | mbarrier | cp floats]
   extern __shared__ __align__(128) float smem[];
   float* box = smem;
-  LiEntry* li_tab = reinterpret_cast<LiEntry*>(smem + NBOX);
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + NBOX + 64);  // [+66] = kbase
-  float* cps = smem + NBOX + 64 + 4;
+  LiEntry* li_tab = reinterpret_cast<LiEntry*>(smem + NBOX);                  // [16]  64 floats
+  LiPair* li_pairs = reinterpret_cast<LiPair*>(smem + NBOX + 64);             // [8]   64 floats
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + NBOX + 128);  // [+130] = kbase
   const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
 
   const int tid = threadIdx.x;
   const int tiles_i = (a.OI + XT - 1) / XT;
   const int b = blockIdx.z / tiles_i;
+  const float* cps = HAS_CP ? a.cp + (int64_t)b * ncp : nullptr;  // global; see walk_column::refresh
   const int ti = blockIdx.z % tiles_i;
   const int i0 = ti * XT, j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
   const int i1 = min(i0 + XT, a.OI) - 1;
@@ -563,15 +581,20 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     constexpr int C1 = BOX * BK, C2 = BK;
     const unsigned koff = (unsigned)(kMagicBits + rec.x) * C1 + (unsigned)(kMagicBits + rec.y) * C2 +
                           (unsigned)(kMagicBits + rec.z);
-    *reinterpret_cast<uint32_t*>(smem + NBOX + 66) = smem_u32(box) - (koff << 2);
+    *reinterpret_cast<uint32_t*>(smem + NBOX + 130) = smem_u32(box) - (koff << 2);
   }
   if (elastic) {
-    const float* gsrc = a.cp + (int64_t)b * ncp;
-    for (int t = tid; t < ncp; t += 256) cps[t] = gsrc[t];
     if (tid < XT) {
       const LerpAxis li = lerp_axis(a.sc_i, a.ni, min(i0 + tid, a.OI - 1));
       const int plane = a.nj * a.nk * 3;
       li_tab[tid] = LiEntry{li.i0 * plane, li.i1 * plane, li.l0, li.l1};
+    } else if (tid >= 32 && tid < 32 + XT / 2) {
+      const int pr = tid - 32;
+      const LerpAxis la = lerp_axis(a.sc_i, a.ni, min(i0 + 2 * pr, a.OI - 1));
+      const LerpAxis lb = lerp_axis(a.sc_i, a.ni, min(i0 + 2 * pr + 1, a.OI - 1));
+      const int plane = a.nj * a.nk * 3;
+      li_pairs[pr] = LiPair{la.i0 * plane, la.i1 * plane, la.l0, lb.l0, la.l1, lb.l1,
+                            (la.i0 == lb.i0 && la.i1 == lb.i1) ? 1 : 0, 0};
     }
   }
   __syncthreads();  // mbarrier init + control grid + li table visible
@@ -590,11 +613,13 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   // wraps; undone by the per-voxel sum.  Read back through shared memory so ptxas sees
   // an opaque value (it otherwise splits off the 0x4B400000*(C1+C2+1) part and re-adds
   // it in front of each of the 8 taps)
-  const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(smem + NBOX + 66);
+  const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(smem + NBOX + 130);
   const bool identity = elastic && m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f &&
                         m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[7] == 0.f && m[8] == 0.f &&
                         m[9] == 0.f && m[10] == 1.f && m[11] == 0.f;
   const int64_t ostride = (int64_t)a.OJ * a.OK;
+  const bool unit_spacing = a.affine_first ? ta.sp_in_one : ta.sp_out_one;
+  const int emode = !elastic ? 0 : (!unit_spacing ? 4 : (!a.affine_first ? 3 : (identity ? 1 : 2)));
 
   for (int c = 0; c < a.C; ++c) {
     if (c > 0 && tid == 0) {
@@ -628,12 +653,24 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     __syncthreads();
     if (active) {
       float* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
-      if (HAS_FILL && !tile_interior)
-        walk_column<BOX, HAS_CP, true, FASTDIV>(a, ta, box, cps, li_tab, m, elastic, identity, kbase, i0,
-                                               i1, oj, ok, a.fill[c], out, ostride);
-      else
-        walk_column<BOX, HAS_CP, false, FASTDIV>(a, ta, box, cps, li_tab, m, elastic, identity, kbase, i0,
-                                                i1, oj, ok, 0.0f, out, ostride);
+      const bool chk = HAS_FILL && !tile_interior;
+#define TIO_WALK(CHK, EM)                                                                            \
+  walk_column<BOX, HAS_CP, CHK, FASTDIV, EM>(a, ta, box, cps, li_tab, li_pairs, m, elastic, identity, \
+                                             kbase, i0, i1, oj, ok, chk ? a.fill[c] : 0.0f, out, ostride)
+      if (HAS_FILL && chk) {
+        if (emode == 0) TIO_WALK(true, 0);
+        else if (emode == 1) TIO_WALK(true, 1);
+        else if (emode == 2) TIO_WALK(true, 2);
+        else if (emode == 3) TIO_WALK(true, 3);
+        else TIO_WALK(true, 4);
+      } else {
+        if (emode == 0) TIO_WALK(false, 0);
+        else if (emode == 1) TIO_WALK(false, 1);
+        else if (emode == 2) TIO_WALK(false, 2);
+        else if (emode == 3) TIO_WALK(false, 3);
+        else TIO_WALK(false, 4);
+      }
+#undef TIO_WALK
     }
     if (c + 1 < a.C) __syncthreads();  // box is reused by the next channel
   }
@@ -724,8 +761,6 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
                          cudaStream_t st) {
   if ((a.K & 3) || ((uintptr_t)a.src & 15)) return 1;   // TMA strides must be 16-byte multiples
   if ((int64_t)a.B * a.C > (1 << 30)) return 1;
-  const size_t ncp = a.cp ? (size_t)a.ni * a.nj * a.nk * 3 : 0;
-  if (ncp * 4 > 32 * 1024) return 1;
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return 1;
   // supported box edges; 0 (auto) = 24
@@ -766,7 +801,7 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
   const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
   if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, records);
   else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, records);
-  const size_t smem = ((size_t)box * box * (box + 4) + 64 + 4 + ncp) * sizeof(float);
+  const size_t smem = ((size_t)box * box * (box + 4) + 128 + 4) * sizeof(float);
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 22) launch_box<22>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, records, st);
