@@ -96,6 +96,18 @@ int tio_resample(const void* src, void* dst, int dtype,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Parameter-table upload without the copy engine: an SM kernel reads `bytes`
+ * from page-locked host memory (`host_pinned`, a cudaHostAlloc/cudaHostRegister
+ * pointer, device-visible under unified addressing) and writes them to
+ * `dst_device`, ordered on `stream` like any launch.  The reference builds these
+ * tables on the host and moves them with `.to(device)` inside each transform
+ * (e.g. spatial.py:1548-1551, blur.py:292-328); when a batch is streamed through
+ * the device in slices, such small cudaMemcpyAsync calls queue behind the bulk
+ * volume copies on the copy engine and stall the kernels that need them.
+ */
+int tio_upload(const void* host_pinned, void* dst_device, size_t bytes, void* stream);
+
+/*
  * Per-channel minimum of batch element 0 -> fill[C] on the device, no host
  * sync.  Replaces _batch_fill_value("minimum") = tensor.min().item()
  * (spatial.py:2054-2060, 2094-2095).  `src` is (B, C, n) fp32, n = I*J*K.

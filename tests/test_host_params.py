@@ -98,3 +98,31 @@ def test_lazy_params_materialise_on_every_read_path():
     q = LazyParams({"a": 1})
     q.set_lazy("m", thunk)
     assert q == {"a": 1, "m": [[1.0, 2.0], None]}
+
+
+def test_slice_params_keeps_shared_entries_and_slices_per_instance_ones():
+    """params.slice_params: the per-element rule of data/batch.py:365-399 over a range."""
+    import torch
+
+    import torchio_b200 as tio
+    from torchio_b200.params import LazyParams, slice_params
+
+    shared = {"std": 0.5, "seed": 7}
+    assert slice_params(shared, 1, 3) is shared
+    p = LazyParams({"std": [0.1, 0.2, 0.3, 0.4], "seed": 11, "_batch_size": 4,
+                    "_batched_keys": ["std", "big"], "_keep": [True, False, True, True]})
+    forced = []
+    p.set_lazy("big", lambda: forced.append(1) or [[0], [1], [2], [3]])
+    q = slice_params(p, 1, 3)
+    assert not forced  # still lazy
+    assert q["std"] == [0.2, 0.3] and q["seed"] == 11 and q["_batch_size"] == 2
+    assert q["_keep"] == [False, True] and q["big"] == [[1], [2]] and forced
+    # spatial params carry their numpy geometry along
+    torch.manual_seed(3)
+    x = torch.zeros((4, 1, 8, 8, 8))
+    batch = tio.SubjectsBatch({"t1": tio.ImagesBatch(x, [tio.AffineMatrix() for _ in range(4)])})
+    t = tio.Affine(scales=(0.9, 1.1), degrees=(-10, 10))
+    params = t.make_params(batch)
+    part = slice_params(params, 2, 4)
+    assert len(part._packed[0]) == 2 and part._packed[2] is True
+    assert part["affine_matrix"] == params["affine_matrix"][2:4]

@@ -129,9 +129,15 @@ def upload(device: torch.device, *arrays):
             continue
         t, off, nbytes = s
         stage_np[off:off + nbytes] = t.reshape(-1).numpy().view(np.uint8)
-    dev = stage.to(device, non_blocking=True)
     if slot is not None:
+        # SM copy kernel instead of cudaMemcpyAsync: see tio_upload in include/tio_b200.h
+        dev = torch.empty(offset, dtype=torch.uint8, device=device)
+        _native.call("tio_upload", stage.data_ptr(), dev.data_ptr(), offset,
+                     torch.cuda.current_stream(dev.device).cuda_stream)
+        _count(1)
         _ring.release(slot, torch.device(device))
+    else:
+        dev = stage.to(device, non_blocking=True)
     out = []
     for s in specs:
         if s is None:

@@ -196,11 +196,14 @@ class LazyParams(dict):
     fast.  Reads (`[]`, ``get``, ``items``, ``values``, ``==``, ``repr``, pickling,
     ``json.dumps``) force the entry, so observable content is identical."""
 
-    __slots__ = ("_lazy",)
+    __slots__ = ("_lazy", "_packed")
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self._lazy = {}
+        #: numpy form of bulky entries kept by ``make_params`` for ``apply_transform``
+        #: (not part of the dict: invisible to ==, json, pickling)
+        self._packed = None
 
     def set_lazy(self, key, thunk) -> None:
         dict.__setitem__(self, key, None)
@@ -264,6 +267,38 @@ class LazyParams(dict):
 
         self._force()
         return _copy.deepcopy(dict(self), memo)
+
+
+def slice_params(params, b0: int, b1: int):
+    """Recorded ``params`` restricted to batch elements ``[b0, b1)``: per-instance
+    entries (``_batched_keys``, ``_keep``) are sliced, shared entries kept.  The
+    same rule the reference applies per element when a batch is unbatched
+    (data/batch.py:365-399).  Lazy entries stay lazy."""
+    batched = dict.get(params, "_batched_keys")
+    if batched is None:
+        return params
+    out = LazyParams()
+    lazy = getattr(params, "_lazy", {})
+    for key in dict.keys(params):
+        if key in lazy:
+            if key in batched:
+                out.set_lazy(key, lambda key=key: params[key][b0:b1])
+            else:
+                out.set_lazy(key, lambda key=key: params[key])
+            continue
+        value = dict.__getitem__(params, key)
+        if key == "_batch_size":
+            value = b1 - b0
+        elif key == "_keep" and value is not None:
+            value = value[b0:b1]
+        elif key in batched and isinstance(value, list):
+            value = value[b0:b1]
+        dict.__setitem__(out, key, value)
+    packed = getattr(params, "_packed", None)
+    if packed is not None:
+        first, second, per_instance = packed
+        out._packed = (first[b0:b1], second[b0:b1], True) if per_instance else packed
+    return out
 
 
 def uniform_from_unit(u, lo: float, hi: float):

@@ -20,6 +20,7 @@ from __future__ import annotations
 import contextlib
 import copy as _copy
 import inspect
+import threading
 import warnings
 from dataclasses import dataclass, field
 from typing import Any
@@ -60,6 +61,38 @@ def execution_device() -> torch.device:
             " there is no CPU fallback (torch.cuda.is_available() is False)"
         )
     return torch.device("cuda", torch.cuda.current_device())
+
+
+@dataclass
+class ChunkInfo:
+    """Set while `Compose` streams a host batch through the device in slices of
+    the batch axis: the transform is being applied to elements ``[b0, b1)`` of a
+    batch of ``total``.  ``cache`` is shared by all slices of one call (values
+    the reference derives from batch element 0, warnings already issued);
+    ``step`` is the position of the transform in the pipeline."""
+
+    b0: int
+    b1: int
+    total: int
+    cache: dict
+    step: int = 0
+
+
+_chunk_local = threading.local()
+
+
+def chunk_info() -> ChunkInfo | None:
+    return getattr(_chunk_local, "info", None)
+
+
+@contextlib.contextmanager
+def chunk_scope(info: ChunkInfo | None):
+    previous = getattr(_chunk_local, "info", None)
+    _chunk_local.info = info
+    try:
+        yield info
+    finally:
+        _chunk_local.info = previous
 
 
 class _Staging:
@@ -118,6 +151,12 @@ class Transform(nn.Module):
     def __init_subclass__(cls, **kwargs: Any) -> None:
         super().__init_subclass__(**kwargs)
         _TRANSFORM_REGISTRY[cls.__name__] = cls
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
+        """True when ``apply_transform`` on a slice of the batch axis (with
+        `params.slice_params` and an active `ChunkInfo`) equals the same rows
+        of the whole-batch result."""
+        return False
 
     def _warn_if_noop(self, *, is_noop: bool, hint: str) -> None:
         if is_noop:

@@ -18,7 +18,7 @@ from torch import Tensor
 from .. import ops, tables
 from ..data import SubjectsBatch
 from ..params import to_nonneg_range, to_range
-from .base import IntensityTransform
+from .base import IntensityTransform, chunk_info
 
 
 def _as_f32(data: Tensor) -> Tensor:
@@ -42,6 +42,9 @@ class BiasField(IntensityTransform):
 
     @property
     def supports_per_instance_p(self) -> bool:
+        return True
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
         return True
 
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
@@ -82,8 +85,15 @@ def _bias_stage(data_shape, affines, std, seed, scale, *, divide: bool):
             f"Per-instance parameters were recorded for {len(std)} elements"
             f" but the batch has {b}"
         )
+    info = chunk_info()
+    if info is not None and not per_element:
+        # one generator draws the coarse fields of the whole batch: keep this slice's rows
+        full = tables.coarse_bias_fields((info.total, *data_shape[1:]), std, seed, scale)
+        coarse = full[info.b0:info.b1].contiguous()
+    else:
+        coarse = tables.coarse_bias_fields(data_shape, std, seed, scale)
     return {
-        "coarse": tables.coarse_bias_fields(data_shape, std, seed, scale),
+        "coarse": coarse,
         "bias_identity": np.asarray([s == 0 for s in std], dtype=np.uint8) if per_element else None,
         "bias_divide": divide,
     }
@@ -120,6 +130,9 @@ class Blur(IntensityTransform):
 
     @property
     def supports_per_instance_p(self) -> bool:
+        return True
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
         return True
 
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
@@ -184,6 +197,13 @@ class Noise(IntensityTransform):
     def supports_per_instance_p(self) -> bool:
         return True
 
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
+        # the device replay of torch's normal stream starts on 16-word boundaries; the
+        # counter-based stream indexes voxels of the tensor it is given
+        if _noise_mode() != "exact":
+            return False
+        return all(int(np.prod(ib.data.shape[1:])) % 16 == 0 for ib in self._get_images(batch).values())
+
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
         seed = int(torch.randint(0, 2**31, (1,)).item())  # drawn first (noise.py:75)
         n = self._resolve_n(batch)
@@ -219,12 +239,20 @@ def _noise_stage_factory(params):
         position allows (multiples of 16), else with torch.randn on the host,
         which the generator object keeps aligned with ``consumed``."""
         n = int(np.prod(shape))
-        start = consumed[0]
+        info = chunk_info()
+        if info is None:
+            start, n_full = consumed[0], n
+        else:  # rows [b0, b1) of a draw over the whole batch
+            per = n // shape[0]
+            start, n_full = consumed[0] + per * info.b0, per * info.total
         on_device = (not ragged[0] and n >= 16 and n % 16 == 0 and start % 16 == 0
-                     and start + n <= ops.MT_MAX_WORDS and device.type == "cuda")
-        if n < 16 or n % 16:
+                     and n_full % 16 == 0 and start + n <= ops.MT_MAX_WORDS
+                     and device.type == "cuda")
+        if info is not None and not on_device:
+            raise RuntimeError("Noise: this batch cannot be streamed in slices (ragged normal stream)")
+        if n_full < 16 or n_full % 16:
             ragged[0] = True  # torch's tail/scalar paths: stay on the host from here on
-        consumed[0] = start + n + (16 if (n >= 16 and n % 16) else 0)
+        consumed[0] += n_full + (16 if (n_full >= 16 and n_full % 16) else 0)
         if on_device:
             return ops.randn_mt19937(params["seed"], start, n, device).view(shape), None
         # host path: fast-forward the CPU generator to `start` if the device path was used
@@ -282,6 +310,9 @@ class Gamma(IntensityTransform):
 
     @property
     def supports_per_instance_p(self) -> bool:
+        return True
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
         return True
 
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:

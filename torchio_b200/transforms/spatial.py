@@ -17,7 +17,6 @@ B-spline orders >= 2, ``label_interpolation="label"``, ``antialias``,
 
 from __future__ import annotations
 
-import threading
 import warnings
 from numbers import Number
 from typing import Any
@@ -30,7 +29,7 @@ from torch.distributions import Distribution
 from .. import ops, tables
 from ..data import AffineMatrix, Image, ImagesBatch, LabelMap, SubjectsBatch
 from ..params import Choice, LazyParams, _ParameterRange, uniform_from_unit
-from .base import SpatialTransform
+from .base import SpatialTransform, chunk_info
 
 _ORDERS = {
     "nearest": 0, "linear": 1, "quadratic": 2, "cubic": 3,
@@ -41,7 +40,6 @@ LABEL_INTERPOLATION = "label"
 _PAD_MODES = ("minimum", "mean", "otsu")
 _SPLINE_ORDER = 3
 
-_packed = threading.local()  # make_params -> apply_transform hand-off (per thread)
 
 
 # ---- argument parsing (messages follow spatial.py:2592-2762) -----------------
@@ -213,6 +211,23 @@ def _check_folding(cp_shape, max_displacement, shape, spacing) -> None:
             RuntimeWarning,
             stacklevel=4,
         )
+
+
+def _folding_warning(cps, max_displacements, out_shape, a_out) -> None:
+    """One warning for the batch: test the largest displacement of any element."""
+    sp_out = np.asarray(a_out.spacing, dtype=np.float64)
+    worst, grid_shape = None, None
+    for index, cp in enumerate(cps):
+        if cp is None:
+            continue
+        disp = max_displacements[index] if max_displacements else None
+        if disp is None:
+            disp = np.abs(cp).reshape(-1, 3).max(axis=0)
+        disp = np.asarray(disp, dtype=np.float64)
+        worst = disp if worst is None else np.maximum(worst, disp)
+        grid_shape = cp.shape[:3]
+    if worst is not None:
+        _check_folding(grid_shape, worst, out_shape, sp_out)
 
 
 def _shape_of(ib: ImagesBatch) -> tuple[int, int, int]:
@@ -458,7 +473,7 @@ class Spatial(SpatialTransform):
             return {"selected_images": []}
         first = next(iter(images.values()))
         shape, affine = _shape_of(first), first.affines[0]
-        params: dict[str, Any] = {
+        params = LazyParams({
             "selected_images": list(images),
             "original": _space_to_json((shape, affine)),
             "affine_first": self.affine_first,
@@ -468,7 +483,7 @@ class Spatial(SpatialTransform):
             "antialias": self.antialias,
             "default_pad_value": self.default_pad_value,
             "default_pad_label": self.default_pad_label,
-        }
+        })
         n = self._resolve_n(batch)
         if n is None:
             forward, cp, max_disp = self._sample_one(shape, affine)
@@ -478,7 +493,7 @@ class Spatial(SpatialTransform):
             params["affine_matrix"] = None if forward is None else forward.tolist()
             params["control_points"] = None if cp is None else cp.tolist()
             params["max_displacement"] = list(max_disp) if max_disp else None
-            _packed.entry = (params, ([forward], [None if cp is None else cp.numpy()], False))
+            params._packed = ([forward], [None if cp is None else cp.numpy()], False)
             return params
         keep = self._keep_mask(batch, n)
         sampled = self._sample_batch_fast(n, keep, shape, affine)
@@ -496,7 +511,6 @@ class Spatial(SpatialTransform):
             forwards, cps, disps = sampled
         if any(f is not None for f in forwards) or any(c is not None for c in cps):
             _check_shared_space(images, shape, affine)
-        params = LazyParams(params)
         params["target"] = _space_to_json(_resolve_target(self.target, batch, shape, affine))
         params.set_lazy("affine_matrix",
                         lambda: [None if f is None else f.tolist() for f in forwards])
@@ -505,8 +519,27 @@ class Spatial(SpatialTransform):
         params["max_displacement"] = disps
         self._tag_batched(params, batch, n, keep,
                           ["affine_matrix", "control_points", "max_displacement"])
-        _packed.entry = (params, (forwards, cps, True))
+        params._packed = (forwards, cps, True)
         return params
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
+        return True
+
+    def plan_checks(self, batch: SubjectsBatch, params: dict[str, Any]) -> None:
+        """Whole-batch host checks of `apply_transform`, run once when the batch is
+        streamed in slices (each slice then skips them)."""
+        names = params.get("selected_images", [])
+        if not names:
+            return
+        mats, cps, per_instance = _unpack_geometry(params)
+        first = batch.images[names[0]]
+        target = _space_from_json(params["target"])
+        out_shape, a_out = (_shape_of(first), first.affines[0]) if target is None else target
+        no_geometry = all(m is None for m in mats) and all(c is None for c in cps)
+        if no_geometry and target is None:
+            return
+        disps = params["max_displacement"]
+        _folding_warning(cps, disps if per_instance else [disps], out_shape, a_out)
 
     def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
         names = params.get("selected_images", [])
@@ -555,9 +588,9 @@ class Spatial(SpatialTransform):
 def _unpack_geometry(params):
     """(affine matrices, control grids, per_instance) as numpy, reusing the
     arrays make_params just produced when ``params`` is that very dict."""
-    entry = getattr(_packed, "entry", None)
-    if entry is not None and entry[0] is params:
-        return entry[1]
+    packed = getattr(params, "_packed", None)
+    if packed is not None:
+        return packed
     per_instance = "affine_matrix" in (params.get("_batched_keys") or [])
     mats, cps = params["affine_matrix"], params["control_points"]
     if not per_instance:
@@ -632,19 +665,9 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
     )
     if packed is None:  # exact no-op: data and affines untouched (spatial.py:579-590)
         return
-    sp_out = np.asarray(a_out.spacing, dtype=np.float64)
-    worst, grid_shape = None, None
-    for index, cp in enumerate(cps):  # one warning for the batch: test the largest displacement
-        if cp is None:
-            continue
-        disp = max_displacements[index] if max_displacements else None
-        if disp is None:
-            disp = np.abs(cp).reshape(-1, 3).max(axis=0)
-        disp = np.asarray(disp, dtype=np.float64)
-        worst = disp if worst is None else np.maximum(worst, disp)
-        grid_shape = cp.shape[:3]
-    if worst is not None:
-        _check_folding(grid_shape, worst, out_shape, sp_out)
+    info = chunk_info()
+    if info is None:  # streamed batches: checked once on the whole batch (Spatial.plan_checks)
+        _folding_warning(cps, max_displacements, out_shape, a_out)
     device = first.data.device
     mat_d, cp_d, flags_d = ops.upload(device, packed.mat, packed.cp, packed.flags)
     box_hint = _box_hint(packed, a_in.spacing, a_out.spacing, out_shape)
@@ -658,7 +681,13 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
             )
         data = ib.data
         native = data if data.dtype in ops.DTYPE_CODES else data.float()
-        fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
+        if info is None:
+            fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
+        elif info.b0 == 0:  # "minimum"/"mean" read batch element 0: the first slice has it
+            fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
+            info.cache[("fill", info.step, name)] = fill
+        else:
+            fill = info.cache[("fill", info.step, name)]
         out = ops.resample(
             native, mat_d, cp_d, flags_d, a_in.spacing, a_out.spacing,
             affine_first=affine_first, mode=ops.NEAREST if interp == "nearest" else ops.LINEAR,
