@@ -19,6 +19,7 @@ namespace tio {
 
 constexpr int MT_N = 624, MT_M = 397, MT_DEG = 19937;
 constexpr int MT_SEQ = MT_DEG + MT_N;  // words needed to apply a jump polynomial
+constexpr int MT_OFFS = (MT_SEQ + 7) / 4 * 4;  // 16-byte aligned start of the staged offsets
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t c) {
   const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
@@ -54,8 +55,8 @@ struct MtJob { int src, dst, slot; };
 __global__ void __launch_bounds__(640)
 mt_jump_kernel(uint32_t* __restrict__ states, const uint16_t* __restrict__ polys, int stride,
                int first, int S2, int fine) {
-  extern __shared__ uint32_t seq[];  // MT_SEQ words, then a staging area of 2048 indices
-  uint16_t* idx = reinterpret_cast<uint16_t*>(seq + MT_SEQ + 8);
+  extern __shared__ __align__(16) uint32_t seq[];  // MT_SEQ words (+pad), then 2048 staged byte offsets
+  uint32_t* offs = seq + MT_OFFS;
   MtJob job;
   if (fine) {
     const int q = first + (int)blockIdx.x, r = q % S2;
@@ -78,14 +79,25 @@ mt_jump_kernel(uint32_t* __restrict__ states, const uint16_t* __restrict__ polys
   }
   const uint16_t* p = polys + (size_t)job.slot * stride;
   const uint32_t count = p[0] | ((uint32_t)p[1] << 16);
+  // out[tid] = XOR over the polynomial's set bits i of seq[i + tid].  The loop is bound
+  // by shared-memory wavefronts (one per warp per term), so everything else is kept off
+  // the LSU: offsets arrive four per broadcast LDS.128, pre-scaled to bytes.
+  const char* mine = reinterpret_cast<const char*>(seq + (tid < MT_N ? tid : 0));
   uint32_t acc = 0;
   for (uint32_t c0 = 0; c0 < count; c0 += 2048) {
     const uint32_t chunk = min(2048u, count - c0);
-    for (uint32_t t = tid; t < chunk; t += blockDim.x) idx[t] = p[2 + c0 + t];
+    for (uint32_t t = tid; t < chunk; t += blockDim.x) offs[t] = (uint32_t)p[2 + c0 + t] << 2;
     __syncthreads();
     if (tid < MT_N) {
-#pragma unroll 8
-      for (uint32_t t = 0; t < chunk; ++t) acc ^= seq[idx[t] + tid];
+      const uint4* o4 = reinterpret_cast<const uint4*>(offs);
+      const uint32_t quads = chunk >> 2;
+#pragma unroll 4
+      for (uint32_t t = 0; t < quads; ++t) {
+        const uint4 o = o4[t];
+        acc ^= *reinterpret_cast<const uint32_t*>(mine + o.x) ^ *reinterpret_cast<const uint32_t*>(mine + o.y);
+        acc ^= *reinterpret_cast<const uint32_t*>(mine + o.z) ^ *reinterpret_cast<const uint32_t*>(mine + o.w);
+      }
+      for (uint32_t t = quads << 2; t < chunk; ++t) acc ^= *reinterpret_cast<const uint32_t*>(mine + offs[t]);
     }
     __syncthreads();
   }
@@ -171,7 +183,7 @@ extern "C" int tio_randn_mt19937(uint64_t seed, uint64_t offset, uint64_t n, flo
   uint32_t* states = (uint32_t*)workspace;
   const uint16_t* polys = (const uint16_t*)((const char*)table + 32);
   mt_seed_kernel<<<1, 32, 0, st>>>((uint32_t)seed, states);
-  const size_t jump_smem = (size_t)(MT_SEQ + 8) * 4 + 2048 * 2;
+  const size_t jump_smem = (size_t)(MT_OFFS + 2048) * 4;
   cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem);
   const int m_lo = (int)(q_lo / S2), m_hi = (int)((q_hi - 1) / S2);
   const int m_first = m_lo > 1 ? m_lo : 1;

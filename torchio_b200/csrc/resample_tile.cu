@@ -37,6 +37,10 @@ struct TileArgs {
   float rcp[3];  // rn(1/hd)
   float hs[3];   // (size-1)/2           (ATen un-normalise multiplier, exact)
   int sp_in_one, sp_out_one;
+  // launch-invariant index arithmetic, done once on the host
+  long long n_in, n_out;      // voxels per input / output channel
+  int tiles_i;                // output tiles along I
+  unsigned inv_tiles_i;       // floor(2^32 / tiles_i) + 1: z / tiles_i == umulhi(z, inv) for z < 2^16
 };
 
 template <int OFFSET>
@@ -198,7 +202,10 @@ tile_bounds_kernel(const ResampleArgs a, const int box, int4* __restrict__ recor
     ilo[ax] = lo;
   }
   const int code = (ok_bounds && outside) ? 2 : (fits ? 1 : 0);
-  records[tile] = make_int4(ilo[0], ilo[1], ilo[2], code | (interior ? 256 : 0));
+  const bool ident = m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f && m[4] == 0.f &&
+                     m[5] == 1.f && m[6] == 0.f && m[7] == 0.f && m[8] == 0.f && m[9] == 0.f &&
+                     m[10] == 1.f && m[11] == 0.f;  // [p,1] @ I^T == p exactly
+  records[tile] = make_int4(ilo[0], ilo[1], ilo[2], code | (interior ? 256 : 0) | (ident ? 512 : 0));
 }
 
 struct LiEntry {  // per output plane of the tile: I-axis lerp of the control grid
@@ -521,10 +528,10 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
 
   const int tid = threadIdx.x;
-  const int tiles_i = (a.OI + XT - 1) / XT;
-  const int b = blockIdx.z / tiles_i;
+  const int tiles_i = ta.tiles_i;
+  const int b = tiles_i == 1 ? (int)blockIdx.z : (int)__umulhi(blockIdx.z, ta.inv_tiles_i);
   const float* cps = HAS_CP ? a.cp + (int64_t)b * ncp : nullptr;  // global; see walk_column::refresh
-  const int ti = blockIdx.z % tiles_i;
+  const int ti = blockIdx.z - b * tiles_i;
   const int i0 = ti * XT, j0 = blockIdx.y * XT, k0 = blockIdx.x * XT;
   const int i1 = min(i0 + XT, a.OI) - 1;
   // lanes 0-15 / 16-31 of a warp take rows DJ apart: with row pitch BK the two
@@ -535,7 +542,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const int jrow = (warp % DJ) + (warp / DJ) * (2 * DJ) + half * DJ;
   const int oj = j0 + jrow, ok = k0 + (tid & 15);
   const bool active = (oj < a.OJ) && (ok < a.OK);
-  const int64_t n_in = (int64_t)a.I * a.J * a.K, n_out = (int64_t)a.OI * a.OJ * a.OK;
+  const int64_t n_in = ta.n_in, n_out = ta.n_out;
   const uint8_t fl = a.flags ? a.flags[b] : 0;
   const float* __restrict__ src = (const float*)a.src + (int64_t)b * a.C * n_in;
   float* __restrict__ dst = (float*)a.dst + (int64_t)b * a.C * n_out;
@@ -549,7 +556,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
         }
     return;
   }
-  const int64_t tile_id = (((int64_t)b * tiles_i + ti) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned tile_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;  // < 2^31 (launcher)
   const int4 rec = __ldg(records + tile_id);
   const int fit_code = rec.w & 255;
   const bool tile_interior = (rec.w & 256) != 0;
@@ -606,17 +613,20 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     return;
   }
 
-  float m[12];
-#pragma unroll
-  for (int t = 0; t < 12; ++t) m[t] = a.mat[b * 12 + t];
   constexpr int C1 = BOX * BK, C2 = BK;
   // wraps; undone by the per-voxel sum.  Read back through shared memory so ptxas sees
   // an opaque value (it otherwise splits off the 0x4B400000*(C1+C2+1) part and re-adds
   // it in front of each of the 8 taps)
   const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(smem + NBOX + 130);
-  const bool identity = elastic && m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f &&
-                        m[4] == 0.f && m[5] == 1.f && m[6] == 0.f && m[7] == 0.f && m[8] == 0.f &&
-                        m[9] == 0.f && m[10] == 1.f && m[11] == 0.f;
+  const bool identity = elastic && (rec.w & 512);  // matrix == I (tile_bounds_kernel)
+  float m[12];
+  if (!identity) {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) m[t] = a.mat[b * 12 + t];
+  } else {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) m[t] = (t % 5 == 0) ? 1.0f : 0.0f;
+  }
   const int64_t ostride = (int64_t)a.OJ * a.OK;
   const bool unit_spacing = a.affine_first ? ta.sp_in_one : ta.sp_out_one;
   const int emode = !elastic ? 0 : (!unit_spacing ? 4 : (!a.affine_first ? 3 : (identity ? 1 : 2)));
@@ -790,11 +800,16 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
     (void)dims;
     fast = fast && fastdiv_admitted(ta.hd[t], st);
   }
+  ta.n_in = (long long)a.I * a.J * a.K;
+  ta.n_out = (long long)a.OI * a.OJ * a.OK;
+  ta.tiles_i = tiles_i;
+  ta.inv_tiles_i = (unsigned)((1ull << 32) / (unsigned)tiles_i) + 1u;
   ta.sp_in_one = (a.sp_in[0] == 1.f && a.sp_in[1] == 1.f && a.sp_in[2] == 1.f);
   ta.sp_out_one = (a.sp_out[0] == 1.f && a.sp_out[1] == 1.f && a.sp_out[2] == 1.f);
 
   dim3 grid((a.OK + XT - 1) / XT, (a.OJ + XT - 1) / XT, (unsigned)(a.B * tiles_i));
   const int64_t n_tiles = (int64_t)grid.x * grid.y * grid.z;
+  if (n_tiles >= (1ll << 31)) return 1;
   // per-tile records live in caller-provided workspace: no allocation, no state kept
   if (!workspace || workspace_bytes < (size_t)n_tiles * sizeof(int4) || ((uintptr_t)workspace & 15)) return 1;
   int4* records = (int4*)workspace;
