@@ -106,6 +106,12 @@ mt_jump_kernel(uint32_t* __restrict__ states, const uint16_t* __restrict__ polys
 
 // One CTA per segment q: stream words [q*L, (q+1)*L) intersected with
 // [offset, offset+n) -> z[word - offset].  320 threads.
+//
+// Per 624-word block: three dependency waves regenerate the block (wave w owns
+// k = 227w + tid; which of its three operands come from the block being written is
+// known per wave, so the waves carry no per-word selects), then 312 threads turn 39
+// 16-word groups into normals.  Blocks that lie wholly inside the window — all but the
+// first and last of a call — take a path without per-thread range checks.
 __global__ void __launch_bounds__(320)
 mt_normal_kernel(const uint32_t* __restrict__ states, int q_first, unsigned long long L,
                  unsigned long long offset, unsigned long long n, float* __restrict__ z) {
@@ -119,39 +125,45 @@ mt_normal_kernel(const uint32_t* __restrict__ states, int q_first, unsigned long
   const uint32_t* w = states + (size_t)q * MT_N;
   for (int t = tid; t < MT_N; t += blockDim.x) s[t] = w[t];
   __syncthreads();
-  // stream word index of the first word produced from this window is seg_begin
+  constexpr int W = MT_N - MT_M;  // 227
+  const int blk = tid >> 3, j = tid & 7;
+  const int pair = 16 * blk + j;  // u[j] of group blk; its partner is 8 words on
+  // positions relative to the segment start fit 32 bits (L = 2^20)
+  const int lo_rel = (int)(lo - seg_begin), hi_rel = (int)(hi - seg_begin);
+  const long long seg_to_z = (long long)seg_begin - (long long)offset;  // < 0 only in the first segment
   int flip = 0;
-  for (unsigned long long word = seg_begin; word < hi; word += MT_N, flip ^= 1) {
-    uint32_t* cur = s + flip * MT_N;
+  for (int base = 0; base < hi_rel; base += MT_N, flip ^= 1) {
+    const uint32_t* cur = s + flip * MT_N;
     uint32_t* nxt = s + (flip ^ 1) * MT_N;
-    // three waves: k in [0,227), [227,454), [454,624)
-#pragma unroll
-    for (int wave = 0; wave < 3; ++wave) {
-      const int k = wave * (MT_N - MT_M) + tid;
-      if (tid < MT_N - MT_M && k < MT_N) {
-        const uint32_t a = cur[k];
-        const uint32_t b = (k + 1 < MT_N) ? cur[k + 1] : nxt[k + 1 - MT_N];
-        const uint32_t c = (k + MT_M < MT_N) ? cur[k + MT_M] : nxt[k + MT_M - MT_N];
-        nxt[k] = mt_twist(a, b, c);
-      }
-      __syncthreads();
+    // wave 0: k in [0,227): x[k], x[k+1], x[k+397] all in the previous block
+    if (tid < W) nxt[tid] = mt_twist(cur[tid], cur[tid + 1], cur[tid + MT_M]);
+    __syncthreads();
+    // wave 1: k in [227,454): x[k+397] = new word k-227
+    if (tid < W) nxt[W + tid] = mt_twist(cur[W + tid], cur[W + tid + 1], nxt[tid]);
+    __syncthreads();
+    // wave 2: k in [454,624): x[k+397] = new word k-227; x[624] = new word 0
+    if (tid < MT_N - 2 * W) {
+      const int k = 2 * W + tid;
+      const uint32_t b = (k + 1 < MT_N) ? cur[k + 1] : nxt[0];
+      nxt[k] = mt_twist(cur[k], b, nxt[k - W]);
     }
-    // 39 complete 16-blocks per 624 words: thread p < 312 owns pair (j, j+8) of block p/8
-    if (tid < 312 && word + MT_N > lo) {
-      const int blk = tid >> 3, j = tid & 7;
-      const unsigned long long t0 = word + 16ull * blk + j;  // stream index of u[j]
-      if (t0 >= lo && t0 + 8 < hi + 8 && t0 < hi) {
-        const float u1 = (float)(mt_temper(nxt[16 * blk + j]) & 0xffffffu) * (1.0f / 16777216.0f);
-        const float u2 = (float)(mt_temper(nxt[16 * blk + j + 8]) & 0xffffffu) * (1.0f / 16777216.0f);
+    __syncthreads();
+    if (tid < 312 && base + MT_N > lo_rel) {
+      const int t0 = base + pair;  // position of u[j] relative to the segment start
+      const bool whole = (base >= lo_rel) && (base + MT_N <= hi_rel);  // CTA-uniform
+      if (whole || (t0 >= lo_rel && t0 < hi_rel)) {
+        const float u1 = (float)(mt_temper(nxt[pair]) & 0xffffffu) * (1.0f / 16777216.0f);
+        const float u2 = (float)(mt_temper(nxt[pair + 8]) & 0xffffffu) * (1.0f / 16777216.0f);
         const float radius = sqrtf(-2.0f * logf(1.0f - u1));
         const float theta = (float)(6.283185307179586 * (double)u2);  // 2.0f * pi<double> * u2
         float sn, cs;
         sincosf(theta, &sn, &cs);
-        z[t0 - offset] = radius * cs;
-        z[t0 - offset + 8] = radius * sn;
+        float* zp = z + (seg_to_z + t0);  // >= 0: t0 >= lo_rel
+        zp[0] = radius * cs;
+        zp[8] = radius * sn;
       }
     }
-    // the next iteration's first wave writes `cur`, which wave 3 above finished reading
+    // the next iteration's first wave writes `cur`, which wave 2 above finished reading
     // before its barrier; the normals above only read `nxt`, which stays intact
   }
 }
