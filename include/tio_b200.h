@@ -96,6 +96,18 @@ int tio_resample(const void* src, void* dst, int dtype,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Patch extraction for the Queue path: gathers `n` patches of size (pi,pj,pk) with
+ * corners `corners[n][3]` (device int32, voxel indices, corner + size <= shape —
+ * validated by the caller) from one volume `src` (C,I,J,K) into a dense block `dst`
+ * (n,C,pi,pj,pk).  `elem_bytes` in {1,2,4,8} (any dtype; bytes are moved verbatim).
+ * Replaces PatchSampler._extract_patch's per-patch views (data/sampler.py:54-67,
+ * 198-223) + the per-patch copies of collate_subjects' torch.stack
+ * (loader.py:15-24) with one pass over the patch bytes.
+ */
+int tio_crop_patches(const void* src, void* dst, int elem_bytes, int C, int I, int J, int K,
+                     int n, const int32_t* corners, int pi, int pj, int pk, void* stream);
+
+/*
  * Parameter-table upload without the copy engine: an SM kernel reads `bytes`
  * from page-locked host memory (`host_pinned`, a cudaHostAlloc/cudaHostRegister
  * pointer, device-visible under unified addressing) and writes them to

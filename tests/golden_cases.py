@@ -185,3 +185,30 @@ CASES = [
 ]
 
 CASES_BY_NAME = {c["name"]: c for c in CASES}
+
+
+# ---- patch path: UniformSampler / Queue / SubjectsLoader -------------
+
+PATCH_CASES = [
+    dict(name="queue_shuffled", num_subjects=5, shape=(20, 24, 28), patch_size=(8, 10, 12),
+         max_length=12, patches_per_volume=4, batch_size=3, shuffle_subjects=True,
+         shuffle_patches=True, seed=11),
+    dict(name="queue_in_order", num_subjects=3, shape=(16, 16, 16), patch_size=(16, 8, 8),
+         max_length=100, patches_per_volume=5, batch_size=4, shuffle_subjects=False,
+         shuffle_patches=False, seed=12),
+]
+PATCH_CASES_BY_NAME = {c["name"]: c for c in PATCH_CASES}
+
+
+def patch_subject_data(case, sid):
+    """(t1 fp32 (2,I,J,K), seg int16 (1,I,J,K), affine 4x4 float64) of subject ``sid``."""
+    import numpy as np
+    import torch
+
+    g = torch.Generator().manual_seed(5000 + 17 * sid + case["seed"])
+    shape = case["shape"]
+    t1 = torch.rand((2, *shape), generator=g)
+    seg = (torch.rand((1, *shape), generator=g) * 5).to(torch.int16)
+    affine = np.diag([1.0, 1.5, 2.0, 1.0])
+    affine[:3, 3] = [10.0 * sid, -5.0, 2.5]
+    return t1, seg, affine

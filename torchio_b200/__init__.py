@@ -2,7 +2,8 @@
 
 Drop-in for the reference's spatial + intensity augmentation chain
 (`Affine`, `ElasticDeformation`, `Spatial`, `BiasField`, `Blur`, `Noise`,
-`Gamma`, `Compose`) on tensor-backed `Subject` / `SubjectsBatch` data.  The
+`Gamma`, `Compose`) and its patch path (`UniformSampler`, `Queue`,
+`SubjectsLoader`) on tensor-backed `Subject` / `SubjectsBatch` data.  The
 tensor math runs in hand-written sm_100a CUDA kernels exposed through the C-ABI
 of ``include/tio_b200.h``; see DESIGN.md and INTEGRATION.md.
 """
@@ -10,6 +11,9 @@ of ``include/tio_b200.h``; see DESIGN.md and INTEGRATION.md.
 from .data import (AffineMatrix, Image, ImagesBatch, LabelMap, ScalarImage, StudiesBatch,
                    Subject, SubjectsBatch)
 from .params import Choice
+from .patches import (ImagesLoader, PatchLocation, PatchSampler, Queue, StudiesLoader,
+                      SubjectsLoader, UniformSampler, collate_images, collate_studies,
+                      collate_subjects)
 from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, ElasticDeformation,
                          Gamma, IntensityTransform, Noise, Spatial, SpatialTransform, Transform,
                          apply_inverse_transform, execution_device, get_inverse_transform,
@@ -19,8 +23,10 @@ __version__ = "0.1.0"
 
 __all__ = [
     "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose",
-    "ElasticDeformation", "Gamma", "Image", "ImagesBatch", "IntensityTransform", "LabelMap",
-    "Noise", "ScalarImage", "Spatial", "SpatialTransform", "StudiesBatch", "Subject",
-    "SubjectsBatch", "Transform", "apply_inverse_transform", "execution_device",
-    "get_inverse_transform", "set_execution_device",
+    "ElasticDeformation", "Gamma", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
+    "LabelMap", "Noise", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
+    "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
+    "SubjectsLoader", "Transform", "UniformSampler", "apply_inverse_transform", "collate_images",
+    "collate_studies", "collate_subjects", "execution_device", "get_inverse_transform",
+    "set_execution_device",
 ]

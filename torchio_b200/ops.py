@@ -201,6 +201,33 @@ def min_sample0(src: Tensor) -> Tensor:
     return fill
 
 
+def crop_patches(volume: Tensor, corners, size) -> Tensor:
+    """Gather ``n`` patches of ``size`` at voxel ``corners`` (n,3) from one volume
+    (C,I,J,K) into a dense (n,C,*size) block in a single launch
+    (data/sampler.py:54-67 + loader.py:15-24)."""
+    _require_cuda(volume, "crop_patches")
+    if volume.ndim != 4:
+        raise ValueError(f"crop_patches expects a (C, I, J, K) volume, got {tuple(volume.shape)}")
+    volume = volume.contiguous()
+    corners = np.ascontiguousarray(np.asarray(corners, dtype=np.int32).reshape(-1, 3))
+    n = corners.shape[0]
+    c, i, j, k = (int(v) for v in volume.shape)
+    pi, pj, pk = (int(v) for v in size)
+    if n == 0:
+        return volume.new_empty((0, c, pi, pj, pk))
+    if corners.min() < 0 or np.any(corners + np.asarray([pi, pj, pk]) > np.asarray([i, j, k])):
+        raise ValueError("crop_patches: a patch extends beyond the volume")
+    (corners_d,) = upload(volume.device, corners)
+    dst = torch.empty((n, c, pi, pj, pk), dtype=volume.dtype, device=volume.device)
+    with torch.cuda.device(volume.device):
+        _native.call(
+            "tio_crop_patches", _ptr(volume), _ptr(dst), volume.element_size(), c, i, j, k, n,
+            _ptr(corners_d), pi, pj, pk, _stream(volume),
+        )
+    _count(1)
+    return dst
+
+
 def bias_field(src: Tensor, coarse: Tensor, identity: Tensor | None, *, divide=False,
                out: Tensor | None = None) -> Tensor:
     """K2 (intensity/bias_field.py:201-255,296-341)."""
