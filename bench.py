@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: skip the nvidia-smi sampler")
+    ap.add_argument("--labels", action="store_true",
+                    help="configs[3] shape: add an int16 LabelMap (nearest-neighbour resample) to every volume")
     return ap.parse_args()
 
 
@@ -167,8 +169,21 @@ def run_b200(args, rank, world, local_rank):
     affines = [tio.AffineMatrix() for _ in range(args.batch)]
     voxels = args.batch * args.size**3
 
+    labels_host = labels_dev = None
+    if args.labels:  # concentric boxes, values 0..4 (SURVEY.md §8d synthetic label)
+        idx = torch.arange(args.size)
+        ring = torch.minimum(idx, args.size - 1 - idx)
+        depth = torch.minimum(torch.minimum(ring[:, None, None], ring[None, :, None]), ring[None, None, :])
+        one = (depth * 5 // max(args.size // 2, 1)).clamp_(0, 4).to(torch.int16)
+        labels_host = one[None, None].expand(args.batch, 1, -1, -1, -1).contiguous().pin_memory()
+        labels_dev = labels_host.to(dev)
+
     def make_batch(tensor):
-        return tio.SubjectsBatch({"t1": tio.ImagesBatch(tensor, list(affines))})
+        images = {"t1": tio.ImagesBatch(tensor, list(affines))}
+        if args.labels:
+            images["seg"] = tio.ImagesBatch(labels_dev if tensor.is_cuda else labels_host, list(affines),
+                                            image_class=tio.LabelMap)
+        return tio.SubjectsBatch(images)
 
     # event hooks around the dominant kernel (K1) inside the real step
     k1_events = []
@@ -237,7 +252,8 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
         assert res.images["t1"].data.device.type == "cpu"
-        e2e = {"ms": e2e_ms, "bytes_in": host.numel() * 4, "bytes_out": host.numel() * 4}
+        moved = host.numel() * 4 + (labels_host.numel() * 2 if args.labels else 0)
+        e2e = {"ms": e2e_ms, "bytes_in": moved, "bytes_out": moved}
         del res
     ops.resample = raw_resample
 
@@ -274,6 +290,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {
             "workload": ("configs[2]: batch %d of 1x%d^3 fp32, Compose(Affine, ElasticDeformation,"
                          " BiasField, Blur, Noise, Gamma) per GPU" % (args.batch, args.size))
+            + (" + int16 LabelMap (nearest)" if args.labels else "")
             if args.workload == "full" else
             ("configs[1]: batch %d of 1x%d^3 fp32, Compose(Affine, ElasticDeformation) per GPU"
              % (args.batch, args.size)),

@@ -383,3 +383,36 @@ def test_streamed_host_batch_equals_one_shot_rows():
     h1 = [(t.name, json.dumps(t.params, sort_keys=True)) for t in one.applied_transforms]
     h2 = [(t.name, json.dumps(t.params, sort_keys=True)) for t in streamed.applied_transforms]
     assert h1 == h2
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int16, torch.int32])
+@pytest.mark.parametrize("elastic", [False, True])
+def test_nearest_tile_path_is_bit_exact_with_general_path(dtype, elastic):
+    """Label maps (nearest) through the TMA tile kernel == the general gather kernel,
+    with and without a fill value, for every tiled label dtype."""
+    from torchio_b200 import ops
+
+    rng = np.random.default_rng(31)
+    g = torch.Generator().manual_seed(9)
+    lab = (torch.rand((3, 2, 40, 48, 64), generator=g) * 100).to(dtype).cuda()
+    mats = []
+    for b in range(3):
+        ang = rng.uniform(-0.2, 0.2, 3)
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        r = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+             @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])) * rng.uniform(0.9, 1.1)
+        c = (np.array(lab.shape[2:]) - 1) / 2
+        m = np.eye(4); m[:3, :3] = r; m[:3, 3] = c - r @ c + rng.uniform(-2, 2, 3)
+        mats.append(m.astype(np.float32)[:3].reshape(12))
+    mat = torch.tensor(np.stack(mats)).cuda()
+    cp = flags = None
+    if elastic:
+        cp = torch.tensor(rng.uniform(-4, 4, (3, 7, 7, 7, 3)).astype(np.float32)).cuda()
+        flags = torch.tensor([2, 2, 0], dtype=torch.uint8).cuda()
+    one = (1.0, 1.0, 1.0)
+    for fill in (None, torch.tensor([7.0, 3.0]).cuda()):
+        kw = dict(affine_first=True, mode=ops.NEAREST, fill=fill)
+        tiled = ops.resample(lab, mat, cp, flags, one, one, **kw)
+        general = ops.resample(lab, mat, cp, flags, one, one, box_hint=-1, **kw)
+        assert torch.equal(tiled, general)
+        assert tiled.dtype == dtype

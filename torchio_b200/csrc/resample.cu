@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ src,
   }
 }
 
-int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, size_t workspace_bytes,
-                         cudaStream_t st);
+int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, int box_hint, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st);
 size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK);
 
 }  // namespace tio
@@ -180,8 +180,8 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   a.affine_first = affine_first;
   a.cp_in_smem = cp && ((size_t)ni * nj * nk * 12 <= 96 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == TIO_F32 && mode == TIO_LINEAR && box_hint >= 0) {
-    const int rc = launch_resample_tile(a, box_hint, workspace, workspace_bytes, st);
+  if (box_hint >= 0) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
+    const int rc = launch_resample_tile(a, dtype, mode, box_hint, workspace, workspace_bytes, st);
     if (rc == 0) {
       TIO_CHECK_LAUNCH();
       return 0;

@@ -50,6 +50,26 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+// nearest mode: one tap of the staged box, moved bit for bit
+template <typename T>
+__device__ __forceinline__ T lds_elem(uint32_t addr) {
+  if (sizeof(T) == 1) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (T)v;
+  } else if (sizeof(T) == 2) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (T)v;
+  } else {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    T out;
+    memcpy(&out, &v, sizeof(T) < 4 ? sizeof(T) : 4);
+    return out;
+  }
+}
+
 template <bool FASTDIV>
 __device__ __forceinline__ float norm_div(float x, float hd, float rcp) {
   if (FASTDIV) {
@@ -111,7 +131,7 @@ __device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts
 // ---------------------------------------------------------------------------
 template <bool HAS_CP>
 __global__ void __launch_bounds__(256)
-tile_bounds_kernel(const ResampleArgs a, const int box, int4* __restrict__ records) {
+tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, int4* __restrict__ records) {
   const int lane = threadIdx.x & 31;
   const int tiles_i = (a.OI + XT - 1) / XT, tiles_j = (a.OJ + XT - 1) / XT, tiles_k = (a.OK + XT - 1) / XT;
   const int64_t n_tiles = (int64_t)a.B * tiles_i * tiles_j * tiles_k;
@@ -196,8 +216,8 @@ tile_bounds_kernel(const ResampleArgs a, const int box, int4* __restrict__ recor
     int lo = (int)floorf(qlo), hi = (int)floorf(qhi) + 1;
     // every corner (floor(u), floor(u)+1) out of bounds on this axis => all padding
     if (hi < 0 || lo > dims[ax] - 1) outside = true;
-    if (ax == 2) lo &= ~3;  // TMA: innermost coordinate must be 16-byte aligned
-    if (hi - lo + 1 > (ax == 2 ? box + 4 : box)) fits = false;
+    if (ax == 2) lo &= ~(kalign - 1);  // TMA: innermost coordinate must be 16-byte aligned
+    if (hi - lo + 1 > (ax == 2 ? box + kalign : box)) fits = false;
     if (lo < 0 || hi > dims[ax] - 1) interior = false;
     ilo[ax] = lo;
   }
@@ -285,15 +305,19 @@ __device__ __forceinline__ f2 norm_div2(f2 x, float hd, float rcp) {
 //   0 no displacement            1 q = p + d (identity matrix, unit spacing)
 //   2 q = M p + d (unit spacing) 3 q = M (p + d) (unit spacing)
 //   4 displacement with non-unit spacing: plane-at-a-time path only
-template <int BOX, bool HAS_CP, bool CHECK, bool FASTDIV, int EMODE>
+//   T/MODE: float + TIO_LINEAR (8 taps, separable lerp) or a label type + TIO_NEAREST
+//   (round-half-even via a round-to-nearest magic add, one tap moved bit for bit;
+//   CHECK is not used with nearest: border tiles with a fill take the general column)
+template <int BOX, typename T, int MODE, bool HAS_CP, bool CHECK, bool FASTDIV, int EMODE>
 __device__ __forceinline__ void walk_column(
-    const ResampleArgs& a, const TileArgs& ta, const float* __restrict__ box,
+    const ResampleArgs& a, const TileArgs& ta, const T* __restrict__ box,
     const float* __restrict__ cps, const LiEntry* __restrict__ li_tab,
     const LiPair* __restrict__ li_pairs, const float m[12],
     const bool elastic, const bool identity, const uint32_t kbase, const int i0, const int i1,
-    const int oj, const int ok, const float fill_c, float* __restrict__ out, const int64_t ostride) {
-  constexpr int BK = BOX + 4;
+    const int oj, const int ok, const float fill_c, T* __restrict__ out, const int64_t ostride) {
+  constexpr int BK = BOX + 16 / (int)sizeof(T);
   constexpr int C1 = BOX * BK, C2 = BK;
+  constexpr int ESH = sizeof(T) == 1 ? 0 : (sizeof(T) == 2 ? 1 : 2);
   const float hd0 = ta.hd[0], hd1 = ta.hd[1], hd2 = ta.hd[2];
   const float rc0 = ta.rcp[0], rc1 = ta.rcp[1], rc2 = ta.rcp[2];
   const float hs0 = ta.hs[0], hs1 = ta.hs[1], hs2 = ta.hs[2];
@@ -355,7 +379,7 @@ __device__ __forceinline__ void walk_column(
   };
 
   // ---- one plane (odd tail, cell changes inside a pair, non-unit spacing) ----
-  auto one = [&](const int oi, float* __restrict__ dst) {
+  auto one = [&](const int oi, T* __restrict__ dst) {
     const float pi = (float)oi;
     float q0, q1, q2;
     if (HAS_CP && elastic) {
@@ -389,6 +413,14 @@ __device__ __forceinline__ void walk_column(
     const float u0 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q0, hd0, rc0), 1.0f), 1.0f), hs0);
     const float u1 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q1, hd1, rc1), 1.0f), 1.0f), hs1);
     const float u2 = __fmul_rn(__fadd_rn(__fsub_rn(norm_div<FASTDIV>(q2, hd2, rc2), 1.0f), 1.0f), hs2);
+    if (MODE == TIO_NEAREST) {
+      // nearbyint(u) via round-to-nearest-even magic add; taps outside the volume are the
+      // zero halo of the box (grid_sample padding_mode="zeros")
+      const int r0 = __float_as_int(__fadd_rn(u0, kMagic)), r1 = __float_as_int(__fadd_rn(u1, kMagic)),
+                r2 = __float_as_int(__fadd_rn(u2, kMagic));
+      *dst = lds_elem<T>(kbase + (((unsigned)r0 * C1 + (unsigned)r1 * C2 + (unsigned)r2) << ESH));
+      return;
+    }
     // floor via round-down magic add: the mantissa holds floor(u)
     const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
     const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2_ = __fsub_rn(s2, kMagic);
@@ -416,7 +448,7 @@ __device__ __forceinline__ void walk_column(
     const float bb1 = __fmaf_rn(hi1, a11 - a10, a10);
     float v = __fmaf_rn(hi0, bb1 - bb0, bb0);
     if (CHECK && use_fill) v = fill_c;
-    *dst = v;
+    *dst = ElemTraits<T>::from_f32(v);
   };
 
   // ---- two planes (oi, oi+1) in packed registers: same operations, lane by lane ----
@@ -467,6 +499,17 @@ __device__ __forceinline__ void walk_column(
     const f2 u0 = mul2(add2(add2(norm_div2<FASTDIV>(q0, hd0, rc0), mone2), one2), bc(hs0));
     const f2 u1 = mul2(add2(add2(norm_div2<FASTDIV>(q1, hd1, rc1), mone2), one2), bc(hs1));
     const f2 u2 = mul2(add2(add2(norm_div2<FASTDIV>(q2, hd2, rc2), mone2), one2), bc(hs2));
+    if (MODE == TIO_NEAREST) {
+      float r0a, r0b, r1a, r1b, r2a, r2b;
+      unpack2(add2(u0, magic2), r0a, r0b); unpack2(add2(u1, magic2), r1a, r1b); unpack2(add2(u2, magic2), r2a, r2b);
+      const unsigned na = (unsigned)__float_as_int(r0a) * C1 + (unsigned)__float_as_int(r1a) * C2 +
+                          (unsigned)__float_as_int(r2a);
+      const unsigned nb = (unsigned)__float_as_int(r0b) * C1 + (unsigned)__float_as_int(r1b) * C2 +
+                          (unsigned)__float_as_int(r2b);
+      out[0] = lds_elem<T>(kbase + (na << ESH));
+      out[ostride] = lds_elem<T>(kbase + (nb << ESH));
+      continue;
+    }
     const f2 s0 = add2_rd(u0, magic2), s1 = add2_rd(u1, magic2), s2 = add2_rd(u2, magic2);
     const f2 f0 = add2(s0, mmagic2), f1 = add2(s1, mmagic2), f2_ = add2(s2, mmagic2);
     const f2 hi0 = sub2(u0, f0), hi1 = sub2(u1, f1), hi2 = sub2(u2, f2_);
@@ -508,23 +551,26 @@ __device__ __forceinline__ void walk_column(
     unpack2(fma2(hi0, sub2(bb1, bb0), bb0), va, vb);
     if (CHECK && fill_a) va = fill_c;
     if (CHECK && fill_b) vb = fill_c;
-    out[0] = va;
-    out[ostride] = vb;
+    out[0] = ElemTraits<T>::from_f32(va);
+    out[ostride] = ElemTraits<T>::from_f32(vb);
   }
 }
 
-template <int BOX, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
+template <int BOX, typename T, int MODE, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
 __global__ void __launch_bounds__(256, 3)
 resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArgs a,
                      const TileArgs ta, const int4* __restrict__ records) {
-  constexpr int BK = BOX + 4;  // inner (K) box extent: room for the 16-byte origin alignment
+  constexpr int BK = BOX + 16 / (int)sizeof(T);  // inner (K) box extent: room for the 16-byte origin alignment
   constexpr int NBOX = BOX * BOX * BK;
-  // layout: [box floats | li table (16 entries) | mbarrier | cp floats]
-  extern __shared__ __align__(128) float smem[];
-  float* box = smem;
-  LiEntry* li_tab = reinterpret_cast<LiEntry*>(smem + NBOX);                  // [16]  64 floats
-  LiPair* li_pairs = reinterpret_cast<LiPair*>(smem + NBOX + 64);             // [8]   64 floats
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + NBOX + 128);  // [+130] = kbase
+  constexpr int BOXBYTES = (NBOX * (int)sizeof(T) + 15) / 16 * 16;
+  constexpr int ESH = sizeof(T) == 1 ? 0 : (sizeof(T) == 2 ? 1 : 2);
+  // layout: [box elements | li table (16 entries) | pair table (8) | mbarrier, kbase]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* box = reinterpret_cast<T*>(smem_raw);
+  float* aux = reinterpret_cast<float*>(smem_raw + BOXBYTES);
+  LiEntry* li_tab = reinterpret_cast<LiEntry*>(aux);                          // [16]  64 floats
+  LiPair* li_pairs = reinterpret_cast<LiPair*>(aux + 64);                     // [8]   64 floats
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(aux + 128);  // [+130] = kbase
   const int ncp = HAS_CP ? a.ni * a.nj * a.nk * 3 : 0;
 
   const int tid = threadIdx.x;
@@ -544,8 +590,8 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const bool active = (oj < a.OJ) && (ok < a.OK);
   const int64_t n_in = ta.n_in, n_out = ta.n_out;
   const uint8_t fl = a.flags ? a.flags[b] : 0;
-  const float* __restrict__ src = (const float*)a.src + (int64_t)b * a.C * n_in;
-  float* __restrict__ dst = (float*)a.dst + (int64_t)b * a.C * n_out;
+  const T* __restrict__ src = (const T*)a.src + (int64_t)b * a.C * n_in;
+  T* __restrict__ dst = (T*)a.dst + (int64_t)b * a.C * n_out;
 
   if (fl & TIO_FLAG_PASSTHROUGH) {
     if (active)
@@ -558,14 +604,15 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   }
   const unsigned tile_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;  // < 2^31 (launcher)
   const int4 rec = __ldg(records + tile_id);
-  const int fit_code = rec.w & 255;
   const bool tile_interior = (rec.w & 256) != 0;
+  // nearest + fill on a tile that touches the border: the per-voxel mask lives in the general column
+  const int fit_code = (MODE == TIO_NEAREST && HAS_FILL && !tile_interior && (rec.w & 255) == 1) ? 0 : (rec.w & 255);
   const bool elastic = HAS_CP && (fl & TIO_FLAG_ELASTIC);
 
   if (fit_code == 2) {  // pre-image entirely outside the volume
     if (active)
       for (int c = 0; c < a.C; ++c) {
-        const float v = HAS_FILL ? a.fill[c] : 0.0f;
+        const T v = HAS_FILL ? ElemTraits<T>::from_f32(a.fill[c]) : (T)0;
         for (int oi = i0; oi <= i1; ++oi)
           dst[c * n_out + ((int64_t)oi * a.OJ + oj) * a.OK + ok] = v;
       }
@@ -576,7 +623,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // first channel's box: in flight while the CTA stages the control grid
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"((uint32_t)(NBOX * sizeof(float)))
+                 "r"((uint32_t)(NBOX * sizeof(T)))
                  : "memory");
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -588,7 +635,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     constexpr int C1 = BOX * BK, C2 = BK;
     const unsigned koff = (unsigned)(kMagicBits + rec.x) * C1 + (unsigned)(kMagicBits + rec.y) * C2 +
                           (unsigned)(kMagicBits + rec.z);
-    *reinterpret_cast<uint32_t*>(smem + NBOX + 130) = smem_u32(box) - (koff << 2);
+    *reinterpret_cast<uint32_t*>(aux + 130) = smem_u32(box) - (koff << ESH);
   }
   if (elastic) {
     if (tid < XT) {
@@ -608,7 +655,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
 
   if (fit_code == 0) {  // general global-memory path for this tile (CTA-uniform branch)
     if (active)
-      general_column<float, TIO_LINEAR, HAS_CP, HAS_FILL>(a, b, elastic, elastic ? cps : nullptr, src,
+      general_column<T, MODE, HAS_CP, HAS_FILL>(a, b, elastic, elastic ? cps : nullptr, src,
                                                           dst, n_in, n_out, i0, i1 + 1, oj, ok);
     return;
   }
@@ -617,7 +664,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   // wraps; undone by the per-voxel sum.  Read back through shared memory so ptxas sees
   // an opaque value (it otherwise splits off the 0x4B400000*(C1+C2+1) part and re-adds
   // it in front of each of the 8 taps)
-  const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(smem + NBOX + 130);
+  const uint32_t kbase = *reinterpret_cast<volatile uint32_t*>(aux + 130);
   const bool identity = elastic && (rec.w & 512);  // matrix == I (tile_bounds_kernel)
   float m[12];
   if (!identity) {
@@ -634,7 +681,7 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   for (int c = 0; c < a.C; ++c) {
     if (c > 0 && tid == 0) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                   "r"((uint32_t)(NBOX * sizeof(float)))
+                   "r"((uint32_t)(NBOX * sizeof(T)))
                    : "memory");
       asm volatile(
           "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -662,18 +709,23 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
     }
     __syncthreads();
     if (active) {
-      float* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
+      T* out = dst + c * n_out + ((int64_t)i0 * a.OJ + oj) * a.OK + ok;
       const bool chk = HAS_FILL && !tile_interior;
 #define TIO_WALK(CHK, EM)                                                                            \
-  walk_column<BOX, HAS_CP, CHK, FASTDIV, EM>(a, ta, box, cps, li_tab, li_pairs, m, elastic, identity, \
+  walk_column<BOX, T, MODE, HAS_CP, CHK, FASTDIV, EM>(a, ta, box, cps, li_tab, li_pairs, m, elastic, identity, \
                                              kbase, i0, i1, oj, ok, chk ? a.fill[c] : 0.0f, out, ostride)
-      if (HAS_FILL && chk) {
-        if (emode == 0) TIO_WALK(true, 0);
-        else if (emode == 1) TIO_WALK(true, 1);
-        else if (emode == 2) TIO_WALK(true, 2);
-        else if (emode == 3) TIO_WALK(true, 3);
-        else TIO_WALK(true, 4);
-      } else {
+      bool walked = false;
+      if constexpr (MODE == TIO_LINEAR && HAS_FILL) {
+        if (chk) {
+          walked = true;
+          if (emode == 0) TIO_WALK(true, 0);
+          else if (emode == 1) TIO_WALK(true, 1);
+          else if (emode == 2) TIO_WALK(true, 2);
+          else if (emode == 3) TIO_WALK(true, 3);
+          else TIO_WALK(true, 4);
+        }
+      }
+      if (!walked) {
         if (emode == 0) TIO_WALK(false, 0);
         else if (emode == 1) TIO_WALK(false, 1);
         else if (emode == 2) TIO_WALK(false, 2);
@@ -734,17 +786,17 @@ static bool fastdiv_admitted(float d, cudaStream_t st) {
   return ok;
 }
 
-template <int BOX, bool HAS_CP, bool FASTDIV>
+template <int BOX, typename T, int MODE, bool HAS_CP, bool FASTDIV>
 static void launch_tile(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
                         size_t smem, const int4* records, cudaStream_t st) {
   if (a.fill) {
-    cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, true, FASTDIV>,
+    cudaFuncSetAttribute(resample_tile_kernel<BOX, T, MODE, HAS_CP, true, FASTDIV>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_tile_kernel<BOX, HAS_CP, true, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
+    resample_tile_kernel<BOX, T, MODE, HAS_CP, true, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
   } else {
-    cudaFuncSetAttribute(resample_tile_kernel<BOX, HAS_CP, false, FASTDIV>,
+    cudaFuncSetAttribute(resample_tile_kernel<BOX, T, MODE, HAS_CP, false, FASTDIV>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_tile_kernel<BOX, HAS_CP, false, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
+    resample_tile_kernel<BOX, T, MODE, HAS_CP, false, FASTDIV><<<grid, 256, smem, st>>>(tm, a, ta, records);
   }
 }
 
@@ -752,11 +804,25 @@ template <int BOX>
 static void launch_box(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
                        size_t smem, bool fast, const int4* records, cudaStream_t st) {
   if (a.cp) {
-    if (fast) launch_tile<BOX, true, true>(tm, a, ta, grid, smem, records, st);
-    else launch_tile<BOX, true, false>(tm, a, ta, grid, smem, records, st);
+    if (fast) launch_tile<BOX, float, TIO_LINEAR, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<BOX, float, TIO_LINEAR, true, false>(tm, a, ta, grid, smem, records, st);
   } else {
-    if (fast) launch_tile<BOX, false, true>(tm, a, ta, grid, smem, records, st);
-    else launch_tile<BOX, false, false>(tm, a, ta, grid, smem, records, st);
+    if (fast) launch_tile<BOX, float, TIO_LINEAR, false, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<BOX, float, TIO_LINEAR, false, false>(tm, a, ta, grid, smem, records, st);
+  }
+}
+
+// nearest-neighbour label maps: the admitted-division variants only (else the caller's
+// general kernel), boxes 24 and 32
+template <typename T>
+static void launch_nearest(int box, const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta,
+                           dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
+  if (box == 24) {
+    if (a.cp) launch_tile<24, T, TIO_NEAREST, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<24, T, TIO_NEAREST, false, true>(tm, a, ta, grid, smem, records, st);
+  } else {
+    if (a.cp) launch_tile<32, T, TIO_NEAREST, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<32, T, TIO_NEAREST, false, true>(tm, a, ta, grid, smem, records, st);
   }
 }
 
@@ -767,25 +833,36 @@ size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK) {
   return tiles * sizeof(int4);
 }
 
-int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, size_t workspace_bytes,
-                         cudaStream_t st) {
-  if ((a.K & 3) || ((uintptr_t)a.src & 15)) return 1;   // TMA strides must be 16-byte multiples
+int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, int box_hint, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+  // fp32 trilinear, or nearest for the 1/2/4-byte label types
+  int esize = 0;
+  if (mode == TIO_LINEAR) esize = dtype == TIO_F32 ? 4 : 0;
+  else esize = dtype == TIO_U8 ? 1 : dtype == TIO_I16 ? 2 : dtype == TIO_I32 ? 4 : 0;
+  if (!esize) return 1;
+  const int kalign = 16 / esize;
+  if (((int64_t)a.K * esize & 15) || ((uintptr_t)a.src & 15)) return 1;   // TMA strides must be 16-byte multiples
   if ((int64_t)a.B * a.C > (1 << 30)) return 1;
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return 1;
   // supported box edges; 0 (auto) = 24
   int box = 24;
   if (box_hint > 0) box = box_hint <= 20 ? 20 : box_hint <= 22 ? 22 : box_hint <= 24 ? 24 : box_hint <= 28 ? 28 : 32;
+  if (mode == TIO_NEAREST) box = box <= 24 ? 24 : 32;
   const int tiles_i = (a.OI + XT - 1) / XT;
   if ((int64_t)a.B * tiles_i > 65535 || (a.OJ + XT - 1) / XT > 65535) return 1;
 
   CUtensorMap tm;
   const cuuint64_t gdim[4] = {(cuuint64_t)a.K, (cuuint64_t)a.J, (cuuint64_t)a.I, (cuuint64_t)a.B * a.C};
-  const cuuint64_t gstride[3] = {(cuuint64_t)a.K * 4, (cuuint64_t)a.J * a.K * 4,
-                                 (cuuint64_t)a.I * a.J * a.K * 4};
-  const cuuint32_t bdim[4] = {(cuuint32_t)box + 4, (cuuint32_t)box, (cuuint32_t)box, 1};
+  const cuuint64_t gstride[3] = {(cuuint64_t)a.K * esize, (cuuint64_t)a.J * a.K * esize,
+                                 (cuuint64_t)a.I * a.J * a.K * esize};
+  const cuuint32_t bdim[4] = {(cuuint32_t)(box + kalign), (cuuint32_t)box, (cuuint32_t)box, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(a.src), gdim, gstride,
+  const CUtensorMapDataType ttype = mode == TIO_LINEAR ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                    : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                    : esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                                 : CU_TENSOR_MAP_DATA_TYPE_INT32;
+  CUresult rc = encode(&tm, ttype, 4, const_cast<void*>(a.src), gdim, gstride,
                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return 1;
@@ -814,9 +891,16 @@ int launch_resample_tile(const ResampleArgs& a, int box_hint, void* workspace, s
   if (!workspace || workspace_bytes < (size_t)n_tiles * sizeof(int4) || ((uintptr_t)workspace & 15)) return 1;
   int4* records = (int4*)workspace;
   const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
-  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, records);
-  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, records);
-  const size_t smem = ((size_t)box * box * (box + 4) + 128 + 4) * sizeof(float);
+  if (mode == TIO_NEAREST && !fast) return 1;
+  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, records);
+  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, records);
+  const size_t smem = ((size_t)box * box * (box + kalign) * esize + 15) / 16 * 16 + (128 + 4) * sizeof(float);
+  if (mode == TIO_NEAREST) {
+    if (dtype == TIO_U8) launch_nearest<uint8_t>(box, tm, a, ta, grid, smem, records, st);
+    else if (dtype == TIO_I16) launch_nearest<int16_t>(box, tm, a, ta, grid, smem, records, st);
+    else launch_nearest<int32_t>(box, tm, a, ta, grid, smem, records, st);
+    return 0;
+  }
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 22) launch_box<22>(tm, a, ta, grid, smem, fast, records, st);
   else if (box == 24) launch_box<24>(tm, a, ta, grid, smem, fast, records, st);

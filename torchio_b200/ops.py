@@ -173,7 +173,9 @@ def resample(
     sp_in = np.asarray(spacing_in, dtype=np.float32)
     sp_out = np.asarray(spacing_out, dtype=np.float32)
     workspace, ws_bytes = None, 0
-    if box_hint >= 0 and src.dtype == torch.float32 and mode == LINEAR:
+    tiled = (src.dtype == torch.float32 and mode == LINEAR) or (
+        mode == NEAREST and src.dtype in (torch.uint8, torch.int16, torch.int32))
+    if box_hint >= 0 and tiled:
         ws_bytes = _native.lib().tio_resample_workspace_bytes(b, oi, oj, ok)
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=src.device)
     with torch.cuda.device(src.device):
