@@ -313,7 +313,7 @@ def run_b200(args, rank, world, local_rank):
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VOXEL_RESAMPLE * voxels,
             "avg_launch_ms": k1_avg_ms,
             "share_of_step": sum(k1_ms) / ms if k1_ms else None,
-            "traffic": None,
+            "traffic": k1_traffic(args),
         },
         "clocks": clocks,
     }
@@ -334,6 +334,15 @@ def run_b200(args, rank, world, local_rank):
 # reference arm / CPU baseline: the oracle's torch-op port = the op sequence
 # the reference executes on the host (oracle/torch_port.py)
 # ----------------------------------------------------------------------------
+
+
+def k1_traffic(args):
+    """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this
+    workload (profiles/r1_k1_traffic.json), or None when the run differs from it."""
+    path = ROOT / "profiles" / "r1_k1_traffic.json"
+    if not path.exists() or args.batch != 32 or args.size != VOL:
+        return None
+    return json.loads(path.read_text()).get("bytes_per_launch")
 
 
 def cpu_reference(args, steps, warmup):
