@@ -108,6 +108,19 @@ int tio_crop_patches(const void* src, void* dst, int elem_bytes, int C, int I, i
                      int n, const int32_t* corners, int pi, int pj, int pk, void* stream);
 
 /*
+ * Flip / Crop / Pad as one index-remap copy of a (B,C,I,J,K) batch into (B,C,OI,OJ,OK):
+ * source index along an axis = output index - off (off = voxels padded before; negative =
+ * voxels cropped), indices outside the volume follow `mode` (0 constant -> `*fill`,
+ * `elem_bytes` bytes on the HOST; 1 replicate; 2 reflect; 3 circular — F.pad's modes),
+ * then the axis is reversed when the element's bit in `flip[b]` is set (bit 0 I, 1 J, 2 K;
+ * device array or NULL).  Replaces torch.flip + torch.where (spatial/flip.py:233-263),
+ * the crop slice (crop.py:84-101) and F.pad (_padding.py:73-104).  Any dtype by size.
+ */
+int tio_remap(const void* src, void* dst, int elem_bytes, int B, int C, int I, int J, int K,
+              int OI, int OJ, int OK, int off_i, int off_j, int off_k, int mode,
+              const void* fill, const uint8_t* flip, void* stream);
+
+/*
  * Parameter-table upload without the copy engine: an SM kernel reads `bytes`
  * from page-locked host memory (`host_pinned`, a cudaHostAlloc/cudaHostRegister
  * pointer, device-visible under unified addressing) and writes them to

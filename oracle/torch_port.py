@@ -416,7 +416,52 @@ def gamma(images: dict, params: dict, invert: bool = False) -> None:
         img["data"] = x.sign() * x.abs().pow(gam)
 
 
+def flip(images: dict, params: dict) -> None:
+    """Flip.apply_transform (spatial/flip.py:186-263): data reversed along the sampled
+    axes, per element when params are per-instance; affines untouched."""
+    axes = params["axes"]
+    per_instance = "_batched_keys" in params
+    for img in images.values():
+        data = img["data"]
+        if per_instance:
+            out = data.clone()
+            for b, ax in enumerate(axes):
+                if ax:
+                    out[b] = torch.flip(data[b], [a - 3 for a in ax])
+            img["data"] = out
+        elif axes:
+            img["data"] = torch.flip(data, [a - 3 for a in axes])
+
+
+def _shift_origin(img: dict, voxels) -> None:
+    shift = np.asarray(voxels, dtype=np.float64)
+    for a in img["affines"]:
+        a[:3, 3] += a[:3, :3] @ shift
+
+
+def crop(images: dict, params: dict) -> None:
+    """Crop.apply_transform (spatial/crop.py:77-101)."""
+    i0, i1, j0, j1, k0, k1 = params["cropping"]
+    for img in images.values():
+        d = img["data"]
+        si, sj, sk = d.shape[-3:]
+        img["data"] = d[..., i0:si - i1 or None, j0:sj - j1 or None, k0:sk - k1 or None].contiguous()
+        _shift_origin(img, (i0, j0, k0))
+
+
+def pad(images: dict, params: dict) -> None:
+    """Pad.apply_transform, non-statistic modes (spatial/pad.py:88-110, _padding.py:83-90)."""
+    i0, i1, j0, j1, k0, k1 = params["padding"]
+    for img in images.values():
+        img["data"] = torch.nn.functional.pad(img["data"], (k0, k1, j0, j1, i0, i1),
+                                              mode=params["padding_mode"], value=params["fill"])
+        _shift_origin(img, (-i0, -j0, -k0))
+
+
 _APPLY = {
+    "Flip": flip,
+    "Crop": crop,
+    "Pad": pad,
     "Spatial": spatial,
     "Affine": spatial,
     "ElasticDeformation": spatial,

@@ -29,7 +29,7 @@ sys.path.insert(2, str(HERE.parent))
 
 import torchio as tio  # noqa: E402  (the reference)
 
-from golden_cases import CASES, build_inputs  # noqa: E402
+from golden_cases import CASES, NEIGHBOUR_CASES, build_inputs  # noqa: E402
 
 
 def _make_transform(spec):
@@ -75,7 +75,8 @@ def run_case(case):
 def main():
     torch.set_num_threads(1)
     out_dir = HERE
-    for case in CASES:
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"   # "neighbours": leave the hot-path fixtures alone
+    for case in (NEIGHBOUR_CASES if only == "neighbours" else CASES + NEIGHBOUR_CASES):
         arrays = run_case(case)
         path = out_dir / f"{case['name']}.npz"
         np.savez_compressed(path, **arrays)

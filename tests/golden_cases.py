@@ -184,7 +184,37 @@ CASES = [
                     ("Gamma", {"log_gamma": (-0.3, 0.3)})]),
 ]
 
-CASES_BY_NAME = {c["name"]: c for c in CASES}
+# ---- index-remap neighbours of the chain: Flip / Crop / Pad ----------
+NEIGHBOUR_CASES = [
+    dict(name="flip_b4_per_instance", seed=81, shape=(10, 12, 14), batch=4,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Flip", {"axes": (0, 1, 2), "flip_probability": 0.5})),
+    dict(name="flip_gated_two_axes", seed=82, shape=(9, 8, 16), batch=5, channels=2,
+         images={"t1": "scalar"}, transform=("Flip", {"axes": (0, 2), "p": 0.6})),
+    dict(name="flip_shared", seed=83, shape=(8, 9, 10), batch=3,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Flip", {"axes": (1, 2), "flip_probability": 0.7, "per_instance": False})),
+    dict(name="crop_aniso", seed=84, shape=(12, 13, 14), batch=2, spacing=(1.0, 1.5, 2.0),
+         origin=(5.0, -3.0, 2.0), tilt=0.2, images={"t1": "scalar", "seg": "int16"},
+         transform=("Crop", {"cropping": (1, 2, 3, 0, 2, 1)})),
+    dict(name="pad_constant", seed=85, shape=(8, 9, 10), batch=2, spacing=(2.0, 1.0, 0.5),
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Pad", {"padding": (2, 1, 0, 3, 1, 2), "fill": 1.5})),
+    dict(name="pad_reflect", seed=86, shape=(8, 9, 10), batch=2, images={"t1": "scalar"},
+         transform=("Pad", {"padding": (3, 2, 1), "padding_mode": "reflect"})),
+    dict(name="pad_replicate", seed=87, shape=(8, 9, 10), batch=1, images={"t1": "scalar", "seg": "int16"},
+         transform=("Pad", {"padding": 4, "padding_mode": "replicate"})),
+    dict(name="pad_circular", seed=88, shape=(8, 9, 10), batch=2, images={"t1": "scalar"},
+         transform=("Pad", {"padding": (2, 3, 4, 5, 6, 7), "padding_mode": "circular"})),
+    dict(name="compose_flip_pad_affine_crop", seed=89, shape=(16, 16, 16), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=[("Flip", {"axes": (0, 1, 2), "flip_probability": 0.5}),
+                    ("Pad", {"padding": (2, 2, 4)}),
+                    ("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)}),
+                    ("Crop", {"cropping": (2, 2, 4)})]),
+]
+
+CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES}
 
 
 # ---- patch path: UniformSampler / Queue / SubjectsLoader -------------

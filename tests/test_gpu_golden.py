@@ -11,7 +11,7 @@ import copy
 import pytest
 import torch
 
-from golden_cases import CASES
+from golden_cases import CASES, NEIGHBOUR_CASES
 from util import load_golden, product_batch, product_replay, report
 
 pytestmark = pytest.mark.gpu
@@ -49,7 +49,53 @@ def test_cuda_matches_reference_golden(name):
             assert abs(a.numpy() - expected_aff[n][b]).max() < 1e-12
 
 
-@pytest.mark.parametrize("name", ["compose_full_b2", "affine_gated", "noise_rician_gated"])
+@pytest.mark.parametrize("name", [c["name"] for c in NEIGHBOUR_CASES])
+def test_cuda_neighbours_match_reference_golden(name):
+    """Flip / Crop / Pad: pure index moves, bit-exact with the reference (the composed
+    case contains an Affine: labels exact, images within the resample tolerance);
+    affines follow the reference's origin shifts; the inverse restores the input."""
+    _, images, history, expected, expected_aff = load_golden(name)
+    batch = product_batch(images, device="cuda")
+    out = product_replay(batch, history)
+    exact = all(h["name"] in ("Flip", "Crop", "Pad") for h in history)
+    for n, exp in expected.items():
+        got = out.images[n].data.cpu()
+        assert got.dtype == exp.dtype and got.shape == exp.shape
+        if exact or images[n]["kind"] == "label":
+            assert torch.equal(got, exp), (n, report(got, exp))
+        else:
+            assert report(got, exp)["max_abs_over_range"] <= TOL_RANGE
+        for b, a in enumerate(out.images[n].affines):
+            assert abs(a.numpy() - expected_aff[n][b]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["flip_b4_per_instance", "crop_aniso", "pad_constant"])
+def test_neighbour_inverse_round_trip(name):
+    import warnings
+
+    from golden_cases import CASES_BY_NAME
+    from util import make_product_transform
+
+    case, images, _, _, _ = load_golden(name)
+    batch = product_batch(images, device="cuda")
+    before = {n: ib.data.clone() for n, ib in batch.images.items()}
+    torch.manual_seed(case["seed"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = make_product_transform(CASES_BY_NAME[name]["transform"])(batch)
+        back = out.apply_inverse_transform()
+    for n, ref in before.items():
+        got = back.images[n].data
+        if name == "crop_aniso":  # cropped voxels come back as padding zeros
+            i0, i1, j0, j1, k0, k1 = case["transform"][1]["cropping"]
+            sl = (..., slice(i0, ref.shape[-3] - i1), slice(j0, ref.shape[-2] - j1), slice(k0, ref.shape[-1] - k1))
+            assert torch.equal(got[sl], ref[sl])
+        else:
+            assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("name", ["compose_full_b2", "affine_gated", "noise_rician_gated",
+                                  "compose_flip_pad_affine_crop", "flip_gated_two_axes"])
 def test_public_call_path_matches_golden(name):
     """Same check through Compose.__call__ with the reference's seed: sampling,
     gating and kernels together."""

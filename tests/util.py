@@ -85,7 +85,8 @@ def blank_transform(name):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return getattr(tio, name)()
+        required = {"Crop": {"cropping": 0}, "Pad": {"padding": 0}}.get(name, {})
+        return getattr(tio, name)(**required)
 
 
 def product_replay(batch, history):

@@ -14,17 +14,17 @@ from .params import Choice
 from .patches import (ImagesLoader, PatchLocation, PatchSampler, Queue, StudiesLoader,
                       SubjectsLoader, UniformSampler, collate_images, collate_studies,
                       collate_subjects)
-from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, ElasticDeformation,
-                         Gamma, IntensityTransform, Noise, Spatial, SpatialTransform, Transform,
+from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Crop,
+                         ElasticDeformation, Flip, Gamma, IntensityTransform, Noise, Pad, Spatial, SpatialTransform, Transform,
                          apply_inverse_transform, execution_device, get_inverse_transform,
                          set_execution_device)
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose",
-    "ElasticDeformation", "Gamma", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
-    "LabelMap", "Noise", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
+    "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose", "Crop",
+    "ElasticDeformation", "Flip", "Gamma", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
+    "LabelMap", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
     "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
     "SubjectsLoader", "Transform", "UniformSampler", "apply_inverse_transform", "collate_images",
     "collate_studies", "collate_subjects", "execution_device", "get_inverse_transform",

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "tio_resample_workspace_bytes": [c_int, c_int, c_int, c_int],
     "tio_min_sample0": [c_void_p, c_int, c_int64, c_void_p, c_void_p],
     "tio_upload": [c_void_p, c_void_p, c_size_t, c_void_p],
+    "tio_remap": [c_void_p, c_void_p, c_int] + [c_int] * 8 + [c_int] * 3 + [c_int, c_void_p, c_void_p, c_void_p],
     "tio_crop_patches": [c_void_p, c_void_p, c_int] + [c_int] * 5 + [c_void_p, c_int, c_int, c_int, c_void_p],
     "tio_bias_field": [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 3
     + [c_void_p, c_int, c_void_p],

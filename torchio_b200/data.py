@@ -79,6 +79,27 @@ class AffineMatrix:
         rz = self._m[:3, :3]
         return rz / np.sqrt(np.sum(rz**2, axis=0))
 
+    @property
+    def orientation(self) -> tuple[str, str, str]:
+        """Anatomical axis codes, e.g. ('R','A','S') (data/affine.py:124-128 = nibabel's
+        aff2axcodes: closest axis permutation/flips of the direction part, via its SVD)."""
+        rzs = self._m[:3, :3].astype(np.float64)
+        zooms = np.sqrt((rzs * rzs).sum(axis=0))
+        zooms[zooms == 0] = 1.0
+        rs = rzs / zooms
+        p, s, qs = np.linalg.svd(rs)
+        keep = s > s.max() * 3 * np.finfo(s.dtype).eps
+        r = p[:, keep] @ qs[keep]
+        labels = (("L", "R"), ("P", "A"), ("I", "S"))
+        codes: list[str | None] = [None, None, None]
+        for in_ax in range(3):
+            col = r[:, in_ax]
+            if not np.allclose(col, 0):
+                out_ax = int(np.argmax(np.abs(col)))
+                codes[in_ax] = labels[out_ax][0] if col[out_ax] < 0 else labels[out_ax][1]
+                r[out_ax, :] = 0
+        return (codes[0], codes[1], codes[2])
+
     def to(self, *args: Any, **kwargs: Any) -> AffineMatrix:
         return self  # host-resident by design
 

@@ -230,6 +230,31 @@ def crop_patches(volume: Tensor, corners, size) -> Tensor:
     return dst
 
 
+PAD_MODES = {"constant": 0, "replicate": 1, "reflect": 2, "circular": 3}
+
+
+def remap(src: Tensor, out_shape, offsets, *, mode: str = "constant", fill=0, flip: Tensor | None = None) -> Tensor:
+    """Flip / Crop / Pad in one pass: ``out[..., o] = src[..., o - offset]`` per spatial
+    axis with F.pad's out-of-range rules, then per-element axis reversal (``flip``: (B,)
+    uint8 cuda, bit 0 I, 1 J, 2 K).  flip.py:233-263, crop.py:84-101, _padding.py:73-104."""
+    _require_cuda(src, "remap")
+    if src.ndim != 5:
+        raise ValueError(f"remap expects (B, C, I, J, K), got {tuple(src.shape)}")
+    src = src.contiguous()
+    b, c, i, j, k = (int(v) for v in src.shape)
+    oi, oj, ok = (int(v) for v in out_shape)
+    dst = torch.empty((b, c, oi, oj, ok), dtype=src.dtype, device=src.device)
+    fill_host = torch.tensor([fill]).to(src.dtype)  # F.pad casts the value to the tensor's dtype
+    with torch.cuda.device(src.device):
+        _native.call(
+            "tio_remap", _ptr(src), _ptr(dst), src.element_size(), b, c, i, j, k, oi, oj, ok,
+            int(offsets[0]), int(offsets[1]), int(offsets[2]), PAD_MODES[mode],
+            fill_host.data_ptr(), _ptr(flip), _stream(src),
+        )
+    _count(1)
+    return dst
+
+
 def bias_field(src: Tensor, coarse: Tensor, identity: Tensor | None, *, divide=False,
                out: Tensor | None = None) -> Tensor:
     """K2 (intensity/bias_field.py:201-255,296-341)."""

@@ -1,0 +1,233 @@
+"""Flip, Crop, Pad — the index-remap neighbours of the augmentation chain
+(host-side mirror of transforms/spatial/flip.py, crop.py, pad.py, _padding.py,
+TorchIO 2.0.0a2).
+
+Same constructor arguments, ``params`` and RNG draws as the reference (Flip draws
+``torch.rand(3)`` per element, spatial/flip.py:133,173); the data movement is one
+`ops.remap` launch per image (flip + crop + pad are the same kernel with different
+offsets), and affines are updated exactly as the reference does (crop/pad shift the
+origin, flip leaves the affine untouched).
+"""
+
+from __future__ import annotations
+
+from collections.abc import Sequence
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..data import SubjectsBatch
+from .base import SpatialTransform
+
+_LABEL_TO_AXIS = {"L": ("L", "R"), "R": ("L", "R"), "A": ("A", "P"), "P": ("A", "P"),
+                  "I": ("I", "S"), "S": ("I", "S")}
+
+
+def _resolve_axes(axes, orientation=None) -> tuple[int, ...]:
+    """ints / anatomical strings -> sorted unique ints in {0,1,2} (flip.py:25-66)."""
+    if isinstance(axes, (int, str)):
+        axes = (axes,)
+    result: list[int] = []
+    for axis in axes:
+        if isinstance(axis, int):
+            if axis not in (0, 1, 2):
+                raise ValueError(f"Axis must be 0, 1, or 2; got {axis}")
+            result.append(axis)
+        elif isinstance(axis, str):
+            letter = axis[0].upper()
+            if letter not in _LABEL_TO_AXIS:
+                raise ValueError(
+                    f"Unknown anatomical label {axis!r}."
+                    " Use L, R, A, P, I, S or full names"
+                    " like 'Left', 'Right', etc."
+                )
+            if orientation is None:
+                raise ValueError(
+                    "Cannot resolve anatomical axis label"
+                    f" {axis!r} without image orientation"
+                )
+            pair = _LABEL_TO_AXIS[letter]
+            for dim, code in enumerate(orientation):
+                if code in pair:
+                    result.append(dim)
+                    break
+        else:
+            raise TypeError(f"Axis must be int or str, got {type(axis).__name__}")
+    return tuple(sorted(set(result)))
+
+
+def _flip_images(transform, batch, axes_per_element) -> None:
+    """axes_per_element: one iterable of spatial axes per batch element."""
+    bits = np.asarray([sum(1 << int(a) for a in set(axes)) for axes in axes_per_element], dtype=np.uint8)
+    if not bits.any():
+        return
+    for ib in transform._get_images(batch).values():
+        (flags,) = ops.upload(ib.data.device, bits)
+        ib.data = ops.remap(ib.data, ib.data.shape[2:], (0, 0, 0), flip=flags)
+
+
+class Flip(SpatialTransform):
+    """Reverse voxel order along spatial axes (flip.py:69-214)."""
+
+    def __init__(self, *, axes: int | str | Sequence[int | str] = 0, flip_probability: float = 1.0,
+                 **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.axes = axes
+        if not 0 <= flip_probability <= 1:
+            raise ValueError(f"flip_probability must be in [0, 1], got {flip_probability}")
+        self.flip_probability = flip_probability
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        images = self._get_images(batch)
+        if not images:
+            return {"axes": ()}
+        first = next(iter(images.values()))
+        n = self._resolve_n(batch)
+        if n is None:
+            orientation = first.affines[0].orientation if first.batch_size > 0 else None
+            resolved = _resolve_axes(self.axes, orientation)
+            mask = torch.rand(3) < self.flip_probability
+            return {"axes": tuple(a for a in resolved if mask[a].item())}
+        keep = self._keep_mask(batch, n)
+        axes_list: list[list[int]] = []
+        for index in range(n):
+            if keep is not None and not keep[index]:
+                axes_list.append([])
+                continue
+            resolved = _resolve_axes(self.axes, first.affines[index].orientation)
+            mask = torch.rand(3) < self.flip_probability
+            axes_list.append([a for a in resolved if mask[a].item()])
+        params = {"axes": axes_list}
+        self._tag_batched(params, batch, n, keep, ["axes"])
+        return params
+
+    @property
+    def supports_per_instance_params(self) -> bool:
+        return True
+
+    @property
+    def supports_per_instance_p(self) -> bool:
+        return True
+
+    def supports_chunks(self, batch: SubjectsBatch) -> bool:
+        return True
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        axes = params["axes"]
+        if self._is_per_instance_params(params):
+            _flip_images(self, batch, axes)
+        elif axes:
+            _flip_images(self, batch, [axes] * batch.batch_size)
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]):
+        """Flip is its own inverse (flip.py:206-214)."""
+        if self._is_per_instance_params(params):
+            return _FlipInverse(axes_per_element=params["axes"], copy=False)
+        return Flip(axes=params["axes"], copy=False)
+
+
+class _FlipInverse(SpatialTransform):
+    def __init__(self, *, axes_per_element, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self._axes_per_element = axes_per_element
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        _flip_images(self, batch, self._axes_per_element)
+        return batch
+
+
+def _parse_six(value, what: str) -> tuple[int, int, int, int, int, int]:
+    """int / 3-tuple / 6-tuple -> (i_ini, i_fin, j_ini, j_fin, k_ini, k_fin) (crop.py:20-33)."""
+    if isinstance(value, int):
+        return (value,) * 6
+    values = list(value)
+    if len(values) == 3:
+        i, j, k = values
+        return (i, i, j, j, k, k)
+    if len(values) == 6:
+        return tuple(values)
+    raise ValueError(f"{what} must have 1, 3, or 6 values, got {len(values)}")
+
+
+def _shift_origins(ib, voxels) -> None:
+    """origin += direction·spacing @ voxels for every affine of the batch (crop.py:96-101)."""
+    shift = np.asarray(voxels, dtype=np.float64)
+    for index, affine in enumerate(ib.affines):
+        matrix = affine.numpy().copy()
+        matrix[:3, 3] = matrix[:3, 3] + matrix[:3, :3] @ shift
+        ib.affines[index] = type(affine)(matrix)
+
+
+class Crop(SpatialTransform):
+    """Remove a border of voxels from each side of the volume (crop.py:36-112)."""
+
+    def __init__(self, *, cropping, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.cropping = _parse_six(cropping, "Cropping")
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        return {"cropping": self.cropping}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        i0, i1, j0, j1, k0, k1 = params["cropping"]
+        for ib in self._get_images(batch).values():
+            si, sj, sk = ib.data.shape[-3:]
+            out = (si - i0 - i1, sj - j0 - j1, sk - k0 - k1)
+            if min(out) <= 0:
+                raise ValueError(f"cropping {tuple(params['cropping'])} leaves no voxels of {(si, sj, sk)}")
+            ib.data = ops.remap(ib.data, out, (-i0, -j0, -k0))
+            _shift_origins(ib, (i0, j0, k0))
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]):
+        return Pad(padding=params["cropping"], copy=False)
+
+
+_PADDING_MODES = ("constant", "reflect", "replicate", "circular", "mean", "median", "minimum")
+
+
+class Pad(SpatialTransform):
+    """Add a border of voxels to each side of the volume (pad.py:37-122)."""
+
+    def __init__(self, *, padding, padding_mode: str = "constant", fill: float = 0, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.padding = _parse_six(padding, "Padding")
+        if padding_mode not in _PADDING_MODES:
+            raise ValueError(f"padding_mode must be one of {_PADDING_MODES}, got {padding_mode!r}")
+        self.padding_mode = padding_mode
+        self.fill = fill
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        return {"padding": self.padding, "padding_mode": self.padding_mode, "fill": self.fill}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        i0, i1, j0, j1, k0, k1 = params["padding"]
+        mode = params["padding_mode"]
+        if mode not in ops.PAD_MODES:
+            raise NotImplementedError(
+                f'padding_mode "{mode}" (whole-volume statistic) is not implemented in torchio_b200'
+            )
+        for ib in self._get_images(batch).values():
+            si, sj, sk = ib.data.shape[-3:]
+            ib.data = ops.remap(ib.data, (si + i0 + i1, sj + j0 + j1, sk + k0 + k1), (i0, j0, k0),
+                                mode=mode, fill=params["fill"])
+            _shift_origins(ib, (-i0, -j0, -k0))
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]):
+        return Crop(cropping=params["padding"], copy=False)
