@@ -29,6 +29,12 @@
 namespace tio {
 
 constexpr int XT = 16;  // output tile edge
+// inner (K) extent of the staged box in elements: BOX plus room for rounding the origin down
+// to a 16-byte boundary, itself rounded up so that a box row is a multiple of 16 bytes
+// (cuTensorMapEncodeTiled rejects other inner extents: BOX = 22 fp32 needs 28, not 26)
+__host__ __device__ constexpr int box_k_extent(int box, int elem_bytes) {
+  return (box + 16 / elem_bytes + 16 / elem_bytes - 1) / (16 / elem_bytes) * (16 / elem_bytes);
+}
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: floor() via round-down add
 constexpr int kMagicBits = 0x4B400000;
 
@@ -131,7 +137,7 @@ __device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts
 // ---------------------------------------------------------------------------
 template <bool HAS_CP>
 __global__ void __launch_bounds__(256)
-tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, int4* __restrict__ records) {
+tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const int bk, int4* __restrict__ records) {
   const int lane = threadIdx.x & 31;
   const int tiles_i = (a.OI + XT - 1) / XT, tiles_j = (a.OJ + XT - 1) / XT, tiles_k = (a.OK + XT - 1) / XT;
   const int64_t n_tiles = (int64_t)a.B * tiles_i * tiles_j * tiles_k;
@@ -217,7 +223,7 @@ tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, int4* 
     // every corner (floor(u), floor(u)+1) out of bounds on this axis => all padding
     if (hi < 0 || lo > dims[ax] - 1) outside = true;
     if (ax == 2) lo &= ~(kalign - 1);  // TMA: innermost coordinate must be 16-byte aligned
-    if (hi - lo + 1 > (ax == 2 ? box + kalign : box)) fits = false;
+    if (hi - lo + 1 > (ax == 2 ? bk : box)) fits = false;
     if (lo < 0 || hi > dims[ax] - 1) interior = false;
     ilo[ax] = lo;
   }
@@ -315,7 +321,7 @@ __device__ __forceinline__ void walk_column(
     const LiPair* __restrict__ li_pairs, const float m[12],
     const bool elastic, const bool identity, const uint32_t kbase, const int i0, const int i1,
     const int oj, const int ok, const float fill_c, T* __restrict__ out, const int64_t ostride) {
-  constexpr int BK = BOX + 16 / (int)sizeof(T);
+  constexpr int BK = box_k_extent(BOX, (int)sizeof(T));
   constexpr int C1 = BOX * BK, C2 = BK;
   constexpr int ESH = sizeof(T) == 1 ? 0 : (sizeof(T) == 2 ? 1 : 2);
   const float hd0 = ta.hd[0], hd1 = ta.hd[1], hd2 = ta.hd[2];
@@ -557,10 +563,10 @@ __device__ __forceinline__ void walk_column(
 }
 
 template <int BOX, typename T, int MODE, bool HAS_CP, bool HAS_FILL, bool FASTDIV>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, (BOX <= 22 && sizeof(T) == 4) ? 4 : 3)
 resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArgs a,
                      const TileArgs ta, const int4* __restrict__ records) {
-  constexpr int BK = BOX + 16 / (int)sizeof(T);  // inner (K) box extent: room for the 16-byte origin alignment
+  constexpr int BK = box_k_extent(BOX, (int)sizeof(T));
   constexpr int NBOX = BOX * BOX * BK;
   constexpr int BOXBYTES = (NBOX * (int)sizeof(T) + 15) / 16 * 16;
   constexpr int ESH = sizeof(T) == 1 ? 0 : (sizeof(T) == 2 ? 1 : 2);
@@ -582,8 +588,8 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   const int i1 = min(i0 + XT, a.OI) - 1;
   // lanes 0-15 / 16-31 of a warp take rows DJ apart: with row pitch BK the two
   // half-warps then hit disjoint banks (DJ * BK == 16 mod 32) for axis-aligned reads
-  // BK = 24, 26, 28, 32, 36 -> DJ = 2, 8, 4, (none: 4), 4
-  constexpr int DJ = (BOX == 20) ? 2 : (BOX == 22) ? 8 : 4;
+  // BK = 24, 28, 28, 32, 36 -> DJ = 2, 4, 4, (none: 4), 4
+  constexpr int DJ = (BOX == 20) ? 2 : 4;
   const int warp = tid >> 5, half = (tid >> 4) & 1;
   const int jrow = (warp % DJ) + (warp / DJ) * (2 * DJ) + half * DJ;
   const int oj = j0 + jrow, ok = k0 + (tid & 15);
@@ -856,7 +862,8 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, int box_hin
   const cuuint64_t gdim[4] = {(cuuint64_t)a.K, (cuuint64_t)a.J, (cuuint64_t)a.I, (cuuint64_t)a.B * a.C};
   const cuuint64_t gstride[3] = {(cuuint64_t)a.K * esize, (cuuint64_t)a.J * a.K * esize,
                                  (cuuint64_t)a.I * a.J * a.K * esize};
-  const cuuint32_t bdim[4] = {(cuuint32_t)(box + kalign), (cuuint32_t)box, (cuuint32_t)box, 1};
+  const int bk = box_k_extent(box, esize);
+  const cuuint32_t bdim[4] = {(cuuint32_t)bk, (cuuint32_t)box, (cuuint32_t)box, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType ttype = mode == TIO_LINEAR ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                     : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
@@ -892,9 +899,9 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, int box_hin
   int4* records = (int4*)workspace;
   const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
   if (mode == TIO_NEAREST && !fast) return 1;
-  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, records);
-  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, records);
-  const size_t smem = ((size_t)box * box * (box + kalign) * esize + 15) / 16 * 16 + (128 + 4) * sizeof(float);
+  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, bk, records);
+  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, bk, records);
+  const size_t smem = ((size_t)box * box * bk * esize + 15) / 16 * 16 + (128 + 4) * sizeof(float);
   if (mode == TIO_NEAREST) {
     if (dtype == TIO_U8) launch_nearest<uint8_t>(box, tm, a, ta, grid, smem, records, st);
     else if (dtype == TIO_I16) launch_nearest<int16_t>(box, tm, a, ta, grid, smem, records, st);
