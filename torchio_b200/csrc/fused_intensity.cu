@@ -652,6 +652,8 @@ march_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int 
 // modular indexing.  Taps are zero-padded to 13 (smaller radii use the same code).
 //   EPI = this is the only pass (no J/K blur): noise and gamma at the store.
 // -------------------------------------------------------------------------
+constexpr int M6_PF = 8;  // cp.async FIFO depth of march6_kernel (power of two)
+
 template <bool HAS_BIAS, bool EPI>
 __global__ void __launch_bounds__(256, EPI ? 1 : 2)
 march6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int I, int J,
@@ -704,8 +706,26 @@ march6_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int
   const int col = j * K + k;  // within one plane
   const int plane = J * K;
 
+  // Input planes arrive through a per-thread cp.async FIFO (M6_PF slots of 16 bytes in shared
+  // memory, no registers): M6_PF-1 loads are in flight per thread while a plane is processed.
+  // Without it the unrolled phases issue one dependent load at a time (8 KB in flight per SM
+  // against the ~35 KB that 6.5 TB/s x DRAM latency needs).  Planes are consumed strictly in
+  // order; slot = plane mod M6_PF; the slot of plane i-1 is refilled while plane i is consumed.
+  float4* fifo = reinterpret_cast<float4*>(g + ((ns + 3) / 4) * 4) + tid;  // [M6_PF][256]
+  auto fifo_issue = [&](int pl) {
+    if (pl < I) {
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(fifo + (pl & (M6_PF - 1)) * 256);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + (int64_t)pl * plane + col) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int pl = 0; pl < M6_PF - 1; ++pl) fifo_issue(pl);
+
   auto load_plane = [&](int i, float* out) {
-    const float4 t = *(const float4*)(x + (int64_t)i * plane + col);
+    fifo_issue(i + M6_PF - 1);  // into the slot of plane i-1 (consumed one call ago)
+    asm volatile("cp.async.wait_group %0;" ::"n"(M6_PF - 1) : "memory");
+    const float4 t = fifo[(i & (M6_PF - 1)) * 256];
     out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
     if (bias_on) {
       const LerpAxis li = lerp_axis(bi.sc_i, bi.si, i);
@@ -892,7 +912,7 @@ static int fused_impl(const float* src, float* dst, float* scratch, int B, int C
     march_kernel<VV, BB><<<grid, block, smem, st>>>(cur, out, B, C, I, J, K, ib, bi, nz1, gamma1); \
   } while (0)
     if (vec && R <= F_R) {
-      const size_t smem6 = (size_t)(16 + (ns + 3) / 4 * 4) * sizeof(float);
+      const size_t smem6 = (size_t)(16 + (ns + 3) / 4 * 4) * sizeof(float) + (size_t)M6_PF * 256 * 16;
 #define TIO_LAUNCH_MARCH6(BB, EE)                                                              \
   do {                                                                                         \
     if (smem6 > 48 * 1024)                                                                     \
