@@ -360,13 +360,12 @@ jk6_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, in
   const int valid = (k < K) ? min(8, J - (j0 + jy)) : 0;
   const int plane_off = (j0 + jy) * K + k;  // within one plane (J*K < 2^31)
 
-  for (int i = i_begin; i < i_end; ++i) {
+  // K pass of one staged plane -> its slot of the double-buffered K-pass plane
+  auto kpass = [&](int i) {
     const int it = i - i_begin, s = it & 1;
-    if (tid == 0 && i + 1 < i_end) issue(i + 1, s ^ 1);  // its last readers passed the previous barrier
     mbar_wait(smem_u32(bars + s), (uint32_t)((it >> 1) & 1));
     float* A = Abuf + s * F_ABUF;
     float* Bw = Bbuf + s * F_BBUF;
-    // ---- K pass ----
 #pragma unroll 1
     for (int r = row_lo + (tid >> 4); r < row_hi; r += 16) {
       float* row = A + min(max(r, rsrc_lo), rsrc_hi) * F_COLS;
@@ -392,7 +391,22 @@ jk6_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, in
       }
       *(float4*)(Bw + r * A_TK + k4) = o4;
     }
-    // normals for this thread's 8 outputs: in flight across the barrier and the J pass
+  };
+
+  // Software pipeline, one barrier per plane: between two barriers every thread runs the
+  // K pass of plane i+1 and then the J pass + store of plane i, so the ragged K-pass rounds
+  // (44 rows over 16 row slots) are amortised over a longer phase and LDS-heavy K work of
+  // some warps overlaps FMA-heavy J work of others.
+  if (tid == 0 && i_begin + 1 < i_end) issue(i_begin + 1, 1);
+  kpass(i_begin);
+  __syncthreads();
+  for (int i = i_begin; i < i_end; ++i) {
+    const int it = i - i_begin, s = it & 1;
+    // plane i+2 replaces plane i in its staging buffer: the K pass of plane i ended before
+    // the barrier that closed the previous phase
+    if (tid == 0 && i + 2 < i_end) issue(i + 2, s);
+    float* Bw = Bbuf + s * F_BBUF;
+    // normals for this thread's 8 outputs: in flight across the K pass of the next plane
     float z1[8], z2[8];
     const int64_t flat0 = (int64_t)bc * n + (int64_t)i * J * K + plane_off;
     if (HAS_EPI && noise_on && nz.mode == 1) {
@@ -412,7 +426,7 @@ jk6_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, in
           if (o < valid) z2[o] = __ldcs(zq);
       }
     }
-    __syncthreads();
+    if (i + 1 < i_end) kpass(i + 1);
     // ---- J pass: thread = (k lane, 8 consecutive j), then epilogue + store ----
     float acc[8];
     switch (rj) {
@@ -467,6 +481,7 @@ jk6_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, in
           if (o < valid) *yp = acc[o];
       }
     }
+    __syncthreads();  // K-pass plane i and staging buffer of plane i+1 are free again
   }
 }
 
