@@ -385,11 +385,12 @@ __device__ __forceinline__ void walk_column(
   };
 
   // ---- one plane (odd tail, cell changes inside a pair, non-unit spacing) ----
-  auto one = [&](const int oi, T* __restrict__ dst) {
-    const float pi = (float)oi;
+  // (`rel` = plane index within the walk, `pi` = its output coordinate as a float: the loop
+  // carries both so that nothing has to be re-derived from blockIdx inside it)
+  auto one = [&](const int rel, const float pi, T* __restrict__ dst) {
     float q0, q1, q2;
     if (HAS_CP && elastic) {
-      const LiEntry li = li_tab[oi - i0];  // warp-uniform broadcast
+      const LiEntry li = li_tab[rel];  // warp-uniform broadcast
       refresh(li);
       float d0 = lerp2(li.l0, r_lo[0], li.l1, r_hi[0]);
       float d1 = lerp2(li.l0, r_lo[1], li.l1, r_hi[1]);
@@ -459,23 +460,28 @@ __device__ __forceinline__ void walk_column(
 
   // ---- two planes (oi, oi+1) in packed registers: same operations, lane by lane ----
   const f2 pj2 = bc(pj), pk2 = bc(pk);
-  int oi = i0;
+  int planes = i1 - i0 + 1;
+  // opaque to the optimiser: otherwise the trip count is re-derived from blockIdx (nine
+  // instructions) in every iteration instead of living in a register
+  asm volatile("" : "+r"(planes));
   f2 pi2 = pack2((float)i0, (float)(i0 + 1));
 #pragma unroll 1
-  for (; oi <= i1; oi += 2, out += 2 * ostride, pi2 = add2(pi2, bc(2.0f))) {
+  for (int rel = 0; rel < planes; rel += 2, out += 2 * ostride, pi2 = add2(pi2, bc(2.0f))) {
     f2 q0, q1, q2;
     // planes go one at a time (single call site, the scalar body is large) when the pair
     // straddles a control cell, at the odd tail, and for EMODE 4 (spacing divides)
-    bool pair_ok = (EMODE != 4) && (oi + 1 <= i1);
+    bool pair_ok = (EMODE != 4) && (rel + 1 < planes);
     LiPair lp;
     if (EMODE != 0 && EMODE != 4) {
-      lp = li_pairs[(oi - i0) >> 1];  // warp-uniform broadcast (two LDS.128)
+      lp = li_pairs[rel >> 1];  // warp-uniform broadcast (two LDS.128)
       pair_ok = pair_ok && lp.same_cell;
     }
     if (!pair_ok) {
-      const int last = min(oi + 1, i1);
+      float pa, pb;
+      unpack2(pi2, pa, pb);
+      const int count = min(2, planes - rel);
 #pragma unroll 1
-      for (int t = oi; t <= last; ++t) one(t, out + (t - oi) * ostride);
+      for (int t = 0; t < count; ++t) one(rel + t, t ? pb : pa, out + t * ostride);
       continue;
     }
     if (EMODE != 0) {
