@@ -214,7 +214,21 @@ NEIGHBOUR_CASES = [
                     ("Crop", {"cropping": (2, 2, 4)})]),
 ]
 
-CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES}
+# transforms whose history holds derived records (CropOrPad leaves Pad + Crop + itself):
+# checked through the public call only, never by replaying the stored history
+CALL_CASES = [
+    dict(name="croporpad_center", seed=91, shape=(14, 9, 12), batch=2, spacing=(1.0, 2.0, 1.5),
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("CropOrPad", {"target_shape": (10, 12, 12)})),
+    dict(name="croporpad_random_mm", seed=92, shape=(16, 10, 12), batch=2, spacing=(1.0, 2.0, 0.5),
+         images={"t1": "scalar"},
+         transform=("CropOrPad", {"target_shape": (12.0, 24.0, 4.0), "units": "mm", "location": "random",
+                                  "padding_mode": "replicate"})),
+    dict(name="croporpad_only_pad", seed=93, shape=(8, 12, 10), batch=1, images={"t1": "scalar", "seg": "int16"},
+         transform=("CropOrPad", {"target_shape": (12, 8, None), "only_pad": True, "fill": 2.5})),
+]
+
+CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES}
 
 
 # ---- patch path: UniformSampler / Queue / SubjectsLoader -------------

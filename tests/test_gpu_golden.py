@@ -11,7 +11,7 @@ import copy
 import pytest
 import torch
 
-from golden_cases import CASES, NEIGHBOUR_CASES
+from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES
 from util import load_golden, product_batch, product_replay, report
 
 pytestmark = pytest.mark.gpu
@@ -67,6 +67,33 @@ def test_cuda_neighbours_match_reference_golden(name):
             assert report(got, exp)["max_abs_over_range"] <= TOL_RANGE
         for b, a in enumerate(out.images[n].affines):
             assert abs(a.numpy() - expected_aff[n][b]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in CALL_CASES])
+def test_croporpad_public_call_matches_reference(name):
+    """CropOrPad through the public call with the reference's seed: bit-exact data, the
+    reference's affines, and the same three history records (Pad, Crop, CropOrPad)."""
+    import json
+    import warnings
+
+    from golden_cases import CASES_BY_NAME
+    from util import make_product_transform
+
+    case = CASES_BY_NAME[name]
+    _, images, history, expected, expected_aff = load_golden(name)
+    batch = product_batch(images, device="cuda")
+    torch.manual_seed(case["seed"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = make_product_transform(case["transform"])(batch)
+    for n, exp in expected.items():
+        got = out.images[n].data.cpu()
+        assert got.dtype == exp.dtype and got.shape == exp.shape
+        assert torch.equal(got, exp), (n, report(got, exp))
+        for b, a in enumerate(out.images[n].affines):
+            assert abs(a.numpy() - expected_aff[n][b]).max() < 1e-12
+    mine = [{"name": t.name, "params": t.params} for t in out.applied_transforms]
+    assert json.loads(json.dumps(mine)) == history
 
 
 @pytest.mark.parametrize("name", ["flip_b4_per_instance", "crop_aniso", "pad_constant"])

@@ -7,7 +7,7 @@ import warnings
 import pytest
 import torch
 
-from golden_cases import CASES, NEIGHBOUR_CASES
+from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES
 from util import load_golden, make_product_transform, product_batch
 
 
@@ -129,3 +129,18 @@ def test_slice_params_keeps_shared_entries_and_slices_per_instance_ones():
     part = slice_params(params, 2, 4)
     assert len(part._packed[0]) == 2 and part._packed[2] is True
     assert part["affine_matrix"] == params["affine_matrix"][2:4]
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in CALL_CASES])
+def test_croporpad_params_match_reference(name):
+    """CropOrPad.make_params (shape arithmetic, units, the torch.randint draws of a random
+    crop) equals the reference's recorded params; the derived Pad / Crop records are
+    checked with the data on the GPU (tests/test_gpu_golden.py)."""
+    case, images, history, _, _ = load_golden(name)
+    batch = product_batch(images)
+    transform = make_product_transform(case["transform"])
+    torch.manual_seed(case["seed"])
+    assert torch.rand(1).item() < 2  # the gate draw of Transform._forward_batch
+    params = transform.make_params(batch)
+    assert json.loads(json.dumps(params)) == history[-1]["params"]
+    assert history[-1]["name"] == "CropOrPad"

@@ -14,7 +14,7 @@ from .params import Choice
 from .patches import (ImagesLoader, PatchLocation, PatchSampler, Queue, StudiesLoader,
                       SubjectsLoader, UniformSampler, collate_images, collate_studies,
                       collate_subjects)
-from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Crop,
+from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Crop, CropOrPad,
                          ElasticDeformation, Flip, Gamma, IntensityTransform, Noise, Pad, Spatial, SpatialTransform, Transform,
                          apply_inverse_transform, execution_device, get_inverse_transform,
                          set_execution_device)
@@ -22,7 +22,7 @@ from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Cro
 __version__ = "0.1.0"
 
 __all__ = [
-    "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose", "Crop",
+    "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose", "Crop", "CropOrPad",
     "ElasticDeformation", "Flip", "Gamma", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
     "LabelMap", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
     "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",

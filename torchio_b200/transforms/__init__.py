@@ -3,11 +3,11 @@ from .base import (AppliedTransform, IntensityTransform, SpatialTransform, Trans
 from .compose import Compose
 from .intensity import BiasField, Blur, Gamma, Noise
 from .inverse import apply_inverse_transform, get_inverse_transform
-from .neighbours import Crop, Flip, Pad
+from .neighbours import Crop, CropOrPad, Flip, Pad
 from .spatial import Affine, ElasticDeformation, Spatial
 
 __all__ = [
-    "Affine", "AppliedTransform", "BiasField", "Blur", "Compose", "Crop", "ElasticDeformation",
+    "Affine", "AppliedTransform", "BiasField", "Blur", "Compose", "Crop", "CropOrPad", "ElasticDeformation",
     "Flip", "Gamma", "IntensityTransform", "Noise", "Pad", "Spatial", "SpatialTransform", "Transform",
     "apply_inverse_transform", "execution_device", "get_inverse_transform",
     "set_execution_device",

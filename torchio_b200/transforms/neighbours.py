@@ -231,3 +231,115 @@ class Pad(SpatialTransform):
 
     def inverse(self, params: dict[str, Any]):
         return Crop(cropping=params["padding"], copy=False)
+
+
+# ---- CropOrPad (spatial/crop_or_pad.py, batched path) --------------------------------
+
+
+def _parse_target_shape(target_shape):
+    """int/float or 3-tuple (None = keep that axis) -> 3-tuple of float|None (crop_or_pad.py:50-66)."""
+    if isinstance(target_shape, (int, float)):
+        return (float(target_shape),) * 3
+    values = list(target_shape)
+    if len(values) == 3:
+        return tuple(None if v is None else float(v) for v in values)
+    raise ValueError(f"target_shape must have 1 or 3 values, got {len(values)}")
+
+
+def _to_voxels(target, units, spacing, current_shape):
+    """Target in voxels / mm / cm -> integer voxels per axis (crop_or_pad.py:69-88)."""
+    result = []
+    for t, sp, cur in zip(target, spacing, current_shape, strict=True):
+        if t is None:
+            result.append(cur)
+        elif units == "voxels":
+            result.append(round(t))
+        else:
+            result.append(round(t * (10.0 if units == "cm" else 1.0) / sp))
+    return tuple(result)
+
+
+def _split_per_axis(diff: int, location: str):
+    """((pad_ini, pad_fin), (crop_ini, crop_fin)) for one axis (crop_or_pad.py:91-107);
+    a random crop position draws one ``torch.randint`` per cropped axis."""
+    import math
+
+    if diff > 0:
+        return (math.ceil(diff / 2), math.floor(diff / 2)), (0, 0)
+    if diff < 0:
+        amount = -diff
+        ini = int(torch.randint(0, amount + 1, (1,)).item()) if location == "random" else math.ceil(amount / 2)
+        return (0, 0), (ini, amount - ini)
+    return (0, 0), (0, 0)
+
+
+class CropOrPad(SpatialTransform):
+    """Crop and/or pad to a target spatial shape (crop_or_pad.py:381-635, tensor-backed
+    batched path).  The reference applies ``Compose([Pad, Crop])`` — two copies and two
+    history records; here both index moves are one `ops.remap` launch per image, and the
+    same ``Pad`` and ``Crop`` records are appended to the history so that replay and
+    inversion behave identically."""
+
+    def __init__(self, target_shape, *, units: str = "voxels", padding_mode: str = "constant",
+                 fill: float = 0, only_crop: bool = False, only_pad: bool = False,
+                 location: str = "center", **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        if only_crop and only_pad:
+            raise ValueError("only_crop and only_pad cannot both be True")
+        if units not in ("voxels", "mm", "cm"):
+            raise ValueError(f"units must be 'voxels', 'mm', or 'cm', got {units!r}")
+        if location not in ("center", "random"):
+            raise ValueError(f"location must be 'center' or 'random', got {location!r}")
+        if padding_mode not in _PADDING_MODES:
+            raise ValueError(f"padding_mode must be one of {_PADDING_MODES}, got {padding_mode!r}")
+        self.target_shape = _parse_target_shape(target_shape)
+        self.units = units
+        self.padding_mode = padding_mode
+        self.fill = fill
+        self.only_crop = only_crop
+        self.only_pad = only_pad
+        self.location = location
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        first = next(iter(batch.images.values()))
+        current = tuple(int(v) for v in first.data.shape[-3:])
+        target = _to_voxels(self.target_shape, self.units, first.affines[0].spacing, current)
+        pad_values: list[int] = []
+        crop_values: list[int] = []
+        for cur, tgt in zip(current, target, strict=True):
+            pad, crop = _split_per_axis(tgt - cur, self.location)
+            pad_values.extend(pad)
+            crop_values.extend(crop)
+        padding = tuple(pad_values) if any(v > 0 for v in pad_values) and not self.only_crop else None
+        cropping = tuple(crop_values) if any(v > 0 for v in crop_values) and not self.only_pad else None
+        return {"padding": padding, "cropping": cropping}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        padding, cropping = params["padding"], params["cropping"]
+        if padding is None and cropping is None:
+            return batch
+        if padding is not None and self.padding_mode not in ops.PAD_MODES:
+            raise NotImplementedError(
+                f'padding_mode "{self.padding_mode}" (whole-volume statistic) is not implemented in torchio_b200'
+            )
+        p = padding or (0,) * 6
+        c = cropping or (0,) * 6
+        for ib in self._get_images(batch).values():
+            si, sj, sk = ib.data.shape[-3:]
+            out = (si + p[0] + p[1] - c[0] - c[1], sj + p[2] + p[3] - c[2] - c[3], sk + p[4] + p[5] - c[4] - c[5])
+            ib.data = ops.remap(ib.data, out, (p[0] - c[0], p[2] - c[2], p[4] - c[4]),
+                                mode=self.padding_mode if padding is not None else "constant", fill=self.fill)
+            _shift_origins(ib, (c[0] - p[0], c[2] - p[2], c[4] - p[4]))
+        # the records Compose([Pad, Crop]) leaves behind (crop_or_pad.py:609-633)
+        from .base import AppliedTransform
+
+        include = None if self.include is None else list(self.include)
+        exclude = None if self.exclude is None else list(self.exclude)
+        if padding is not None:
+            batch.applied_transforms.append(AppliedTransform(
+                name="Pad", params={"padding": tuple(padding), "padding_mode": self.padding_mode, "fill": self.fill},
+                include=include, exclude=exclude))
+        if cropping is not None:
+            batch.applied_transforms.append(AppliedTransform(
+                name="Crop", params={"cropping": tuple(cropping)}, include=include, exclude=exclude))
+        return batch
