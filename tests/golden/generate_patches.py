@@ -72,7 +72,36 @@ def run_case(case):
     }
 
 
+def run_samplers():
+    """Weighted / label / grid samplers on one subject (subject 0 of the first case + a
+    probability map): corners drawn, patch sums, grid locations with and without padding."""
+    case = PATCH_CASES[0]
+    t1, seg, affine = patch_subject_data(case, 0)
+    g = torch.Generator().manual_seed(77)
+    prob = torch.rand((1, *case["shape"]), generator=g) ** 4
+    subject = tio.Subject(t1=tio.ScalarImage(t1, affine=affine.copy()), seg=tio.LabelMap(seg, affine=affine.copy()),
+                          prob=tio.ScalarImage(prob, affine=affine.copy()))
+    out = {}
+    torch.manual_seed(5)
+    ws = tio.WeightedSampler(subject, patch_size=case["patch_size"], probability_map="prob")
+    out["weighted"] = [[list(p.patch_location.index), float(p.t1.data.double().sum())] for p in ws(subject, 6)]
+    torch.manual_seed(6)
+    ls = tio.LabelSampler(subject, patch_size=case["patch_size"], label_name="seg", label_probabilities={1: 1.0, 3: 2.0})
+    out["label_probs"] = [[list(p.patch_location.index), float(p.seg.data.double().sum())] for p in ls(subject, 6)]
+    torch.manual_seed(7)
+    ls2 = tio.LabelSampler(subject, patch_size=case["patch_size"], label_name="seg")
+    out["label_default"] = [list(p.patch_location.index) for p in ls2(subject, 4)]
+    gs = tio.GridSampler(subject, patch_size=case["patch_size"], patch_overlap=(2, 4, 4))
+    out["grid"] = [[list(loc.index), float(gs[i].t1.data.double().sum())] for i, loc in enumerate(gs.locations)]
+    gp = tio.GridSampler(subject, patch_size=case["patch_size"], patch_overlap=(2, 4, 4), padding_mode="reflect")
+    out["grid_padded_shape"] = list(gp.subject.spatial_shape)
+    out["grid_padded"] = [[list(loc.index), float(gp[i].t1.data.double().sum())] for i, loc in enumerate(gp.locations)]
+    (HERE / "patches_samplers.json").write_text(json.dumps(out))
+    print("patches_samplers.json", len(json.dumps(out)), "bytes")
+
+
 def main():
+    run_samplers()
     for case in PATCH_CASES:
         arrays = run_case(case)
         path = HERE / f"patches_{case['name']}.npz"

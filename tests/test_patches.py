@@ -135,3 +135,67 @@ def test_threaded_queue_yields_the_same_patch_multiset():
         tio.Queue(subjects, sampler, shuffle_subjects=True, subject_sampler=[0, 1])
     with pytest.raises(ValueError):
         tio.SubjectsLoader(q, collate_fn=lambda b: b)
+
+
+def _sampler_subject(device="cpu"):
+    import torchio_b200 as tio
+
+    case = PATCH_CASES[0]
+    t1, seg, affine = patch_subject_data(case, 0)
+    g = torch.Generator().manual_seed(77)
+    prob = torch.rand((1, *case["shape"]), generator=g) ** 4
+    return case, tio.Subject(t1=tio.ScalarImage(t1.to(device), affine=affine.copy()),
+                             seg=tio.LabelMap(seg.to(device), affine=affine.copy()),
+                             prob=tio.ScalarImage(prob.to(device), affine=affine.copy()))
+
+
+def _check_samplers(device):
+    import torchio_b200 as tio
+
+    gold = json.loads((GOLDEN / "patches_samplers.json").read_text())
+    case, subject = _sampler_subject(device)
+    size = case["patch_size"]
+    torch.manual_seed(5)
+    ws = tio.WeightedSampler(subject, patch_size=size, probability_map="prob")
+    got = [[list(p.patch_location.index), float(p.t1.data.double().sum())] for p in ws.sample(subject, 6)]
+    assert [g[0] for g in got] == [w[0] for w in gold["weighted"]]
+    assert [g[1] for g in got] == pytest.approx([w[1] for w in gold["weighted"]], rel=1e-12)
+    torch.manual_seed(5)
+    assert [list(p.patch_location.index) for p in ws(subject, 6)] == [w[0] for w in gold["weighted"]]
+    torch.manual_seed(6)
+    ls = tio.LabelSampler(subject, patch_size=size, label_name="seg", label_probabilities={1: 1.0, 3: 2.0})
+    got = [[list(p.patch_location.index), float(p.seg.data.double().sum())] for p in ls(subject, 6)]
+    assert got == gold["label_probs"]
+    torch.manual_seed(7)
+    ls2 = tio.LabelSampler(subject, patch_size=size, label_name="seg")
+    assert [list(p.patch_location.index) for p in ls2.sample(subject, 4)] == gold["label_default"]
+    gs = tio.GridSampler(subject, patch_size=size, patch_overlap=(2, 4, 4))
+    assert len(gs) == len(gold["grid"])
+    for i, (index, total) in enumerate(gold["grid"]):
+        assert list(gs.locations[i].index) == index
+        assert float(gs[i].t1.data.double().sum()) == pytest.approx(total, rel=1e-12)
+    return gold, subject, size
+
+
+def test_weighted_label_grid_samplers_match_reference_on_host():
+    _check_samplers("cpu")
+    with pytest.raises(RuntimeError):
+        import torchio_b200 as tio
+
+        _, subject = _sampler_subject()
+        zero = tio.Subject(t1=subject.t1, prob=tio.ScalarImage(torch.zeros_like(subject.prob.data)))
+        next(iter(tio.WeightedSampler(zero, patch_size=4, probability_map="prob")(zero, 1)))
+
+
+@pytest.mark.gpu
+def test_weighted_label_grid_samplers_match_reference_on_device():
+    """Device-resident subject: same draws (the map is sampled on the host), patches gathered
+    by tio_crop_patches; the padded grid goes through the Pad kernel."""
+    import torchio_b200 as tio
+
+    gold, subject, size = _check_samplers("cuda")
+    gp = tio.GridSampler(subject, patch_size=size, patch_overlap=(2, 4, 4), padding_mode="reflect")
+    assert list(gp.subject.spatial_shape) == gold["grid_padded_shape"]
+    for i, (index, total) in enumerate(gold["grid_padded"]):
+        assert list(gp.locations[i].index) == index
+        assert float(gp[i].t1.data.double().sum()) == pytest.approx(total, rel=1e-12)

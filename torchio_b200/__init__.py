@@ -11,8 +11,8 @@ of ``include/tio_b200.h``; see DESIGN.md and INTEGRATION.md.
 from .data import (AffineMatrix, Image, ImagesBatch, LabelMap, ScalarImage, StudiesBatch,
                    Subject, SubjectsBatch)
 from .params import Choice
-from .patches import (ImagesLoader, PatchLocation, PatchSampler, Queue, StudiesLoader,
-                      SubjectsLoader, UniformSampler, collate_images, collate_studies,
+from .patches import (GridSampler, ImagesLoader, LabelSampler, PatchLocation, PatchSampler, Queue,
+                      StudiesLoader, SubjectsLoader, UniformSampler, WeightedSampler, collate_images, collate_studies,
                       collate_subjects)
 from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Crop, CropOrPad,
                          ElasticDeformation, Flip, Gamma, IntensityTransform, Noise, Pad, Spatial, SpatialTransform, Transform,
@@ -23,10 +23,10 @@ __version__ = "0.1.0"
 
 __all__ = [
     "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose", "Crop", "CropOrPad",
-    "ElasticDeformation", "Flip", "Gamma", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
-    "LabelMap", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
+    "ElasticDeformation", "Flip", "Gamma", "GridSampler", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
+    "LabelMap", "LabelSampler", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
     "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
-    "SubjectsLoader", "Transform", "UniformSampler", "apply_inverse_transform", "collate_images",
+    "SubjectsLoader", "Transform", "UniformSampler", "WeightedSampler", "apply_inverse_transform", "collate_images",
     "collate_studies", "collate_subjects", "execution_device", "get_inverse_transform",
     "set_execution_device",
 ]

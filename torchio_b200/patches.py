@@ -141,6 +141,145 @@ class UniformSampler(PatchSampler, IterableDataset):
         return (_rand(0), _rand(1), _rand(2))
 
 
+class GridSampler(PatchSampler, Dataset):
+    """Patches on a regular grid for dense inference (data/sampler.py:70-162)."""
+
+    def __init__(self, subject: Subject, patch_size, patch_overlap=0, padding_mode: str | None = None,
+                 fill: float = 0) -> None:
+        super().__init__(patch_size)
+        if isinstance(patch_overlap, int):
+            patch_overlap = (patch_overlap, patch_overlap, patch_overlap)
+        self.patch_overlap = tuple(int(v) for v in patch_overlap)
+        self.padding_mode = padding_mode
+        self.fill = fill
+        self.subject = self._maybe_pad(subject)
+        self.locations = self._compute_locations(self.subject.spatial_shape)
+
+    def __len__(self) -> int:
+        return len(self.locations)
+
+    def __getitem__(self, index: int) -> Subject:
+        return self._extract_patch(self.subject, self.locations[index])
+
+    def _maybe_pad(self, subject: Subject) -> Subject:
+        if self.padding_mode is None:
+            return subject
+        from .transforms.neighbours import Pad
+
+        border = tuple(v // 2 for v in self.patch_overlap)
+        padding = (border[0], border[0], border[1], border[1], border[2], border[2])
+        return Pad(padding=padding, padding_mode=self.padding_mode, fill=self.fill, copy=False)(subject)
+
+    def _compute_locations(self, spatial_shape) -> list[PatchLocation]:
+        per_axis: list[list[int]] = []
+        for dim in range(3):
+            size, patch, overlap = spatial_shape[dim], self.patch_size[dim], self.patch_overlap[dim]
+            step = max(patch - overlap, 1)
+            indices = list(range(0, size - patch + 1, step))
+            if not indices or indices[-1] != size - patch:
+                indices.append(max(size - patch, 0))
+            per_axis.append(indices)
+        return [PatchLocation(index=(i, j, k), size=self.patch_size)
+                for i in per_axis[0] for j in per_axis[1] for k in per_axis[2]]
+
+
+def _mask_borders(prob: torch.Tensor, spatial_shape, patch_size) -> torch.Tensor:
+    """Zero probability where a patch centre cannot be placed (data/sampler.py:340-360)."""
+    prob = prob.clone()
+    for d in range(3):
+        half = patch_size[d] // 2
+        if half > 0:
+            lo: list[slice] = [slice(None)] * 3
+            lo[d] = slice(0, half)
+            prob[tuple(lo)] = 0
+        tail = spatial_shape[d] - half
+        if tail < spatial_shape[d]:
+            hi: list[slice] = [slice(None)] * 3
+            hi[d] = slice(tail, None)
+            prob[tuple(hi)] = 0
+    return prob
+
+
+def _center_to_corner(center, spatial_shape, patch_size) -> tuple[int, int, int]:
+    """Centre voxel -> patch corner, clamped into the volume (data/sampler.py:363-375)."""
+    result = []
+    for d in range(3):
+        corner = max(0, center[d] - patch_size[d] // 2)
+        result.append(min(corner, spatial_shape[d] - patch_size[d]))
+    return (result[0], result[1], result[2])
+
+
+class WeightedSampler(PatchSampler, IterableDataset):
+    """Random patches weighted by a probability map (data/sampler.py:226-283).
+
+    The centre voxels are drawn with ``torch.multinomial`` on the flattened map.  For a
+    device-resident subject the map is brought to the host once per subject and drawn there,
+    so the draws are those of the reference (global CPU generator), whatever the device."""
+
+    def __init__(self, subject: Subject, patch_size, probability_map: str, num_patches: int | None = None) -> None:
+        super().__init__(patch_size)
+        self.subject = subject
+        self.probability_map = probability_map
+        self.num_patches = num_patches
+
+    def _flat_map(self, subject: Subject):
+        prob = self._build_probability_map_for(subject)
+        flat = prob.flatten()
+        if flat.sum() == 0:
+            raise RuntimeError(f"Probability map '{self.probability_map}' is all zeros")
+        return flat.cpu(), tuple(prob.shape)
+
+    def _draw(self, flat, shape, subject: Subject) -> PatchLocation:
+        idx_flat = torch.multinomial(flat, 1).item()
+        center = tuple(int(x) for x in np.unravel_index(int(idx_flat), shape))
+        return PatchLocation(index=_center_to_corner(center, subject.spatial_shape, self.patch_size),
+                             size=self.patch_size)
+
+    def __call__(self, subject: Subject, num_patches: int | None = None) -> Iterator[Subject]:
+        flat, shape = self._flat_map(subject)
+        limit = num_patches or self.num_patches
+        count = 0
+        while limit is None or count < limit:
+            yield self._extract_patch(subject, self._draw(flat, shape, subject))
+            count += 1
+
+    def __iter__(self) -> Iterator[Subject]:
+        return self(self.subject, self.num_patches)
+
+    def sample(self, subject: Subject, num_patches: int) -> list[Subject]:
+        """``list(islice(self(subject), num_patches))``, same draws, one gather launch per
+        image for a device-resident subject."""
+        flat, shape = self._flat_map(subject)
+        return self._extract_patches(subject, [self._draw(flat, shape, subject) for _ in range(num_patches)])
+
+    def _build_probability_map_for(self, subject: Subject) -> torch.Tensor:
+        prob_data = subject.images[self.probability_map].data[0].float()
+        return _mask_borders(prob_data, subject.spatial_shape, self.patch_size)
+
+    def _build_probability_map(self) -> torch.Tensor:
+        return self._build_probability_map_for(self.subject)
+
+
+class LabelSampler(WeightedSampler):
+    """Random patches centred on labelled voxels (data/sampler.py:286-333)."""
+
+    def __init__(self, subject: Subject, patch_size, label_name: str,
+                 label_probabilities: dict[int, float] | None = None, num_patches: int | None = None) -> None:
+        super().__init__(subject, patch_size, probability_map=label_name, num_patches=num_patches)
+        self.label_name = label_name
+        self.label_probabilities = label_probabilities
+
+    def _build_probability_map_for(self, subject: Subject) -> torch.Tensor:
+        label_data = subject.images[self.label_name].data[0]
+        if self.label_probabilities is not None:
+            prob = torch.zeros_like(label_data, dtype=torch.float32)
+            for label, weight in self.label_probabilities.items():
+                prob[label_data == label] = weight
+        else:
+            prob = (label_data > 0).float()
+        return _mask_borders(prob, subject.spatial_shape, self.patch_size)
+
+
 class Queue(IterableDataset):
     """Patch buffer for stochastic patch-based training (data/queue.py:21-208)."""
 
