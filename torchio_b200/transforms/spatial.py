@@ -523,7 +523,9 @@ class Spatial(SpatialTransform):
         return params
 
     def supports_chunks(self, batch: SubjectsBatch) -> bool:
-        return True
+        # a target space changes shape/affine, which later children's make_params read;
+        # streamed execution samples every child on the batch as it enters the pipeline
+        return self.target is None
 
     def plan_checks(self, batch: SubjectsBatch, params: dict[str, Any]) -> None:
         """Whole-batch host checks of `apply_transform`, run once when the batch is
