@@ -598,7 +598,10 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
   constexpr int DJ = (BOX == 20) ? 2 : 4;
   const int warp = tid >> 5, half = (tid >> 4) & 1;
   const int jrow = (warp % DJ) + (warp / DJ) * (2 * DJ) + half * DJ;
-  const int oj = j0 + jrow, ok = k0 + (tid & 15);
+  int oj = j0 + jrow, ok = k0 + (tid & 15);
+  // kept in registers across the TMA wait (opaque to the optimiser, which otherwise
+  // re-derives them from threadIdx/blockIdx after the barrier)
+  asm volatile("" : "+r"(oj), "+r"(ok));
   const bool active = (oj < a.OJ) && (ok < a.OK);
   const int64_t n_in = ta.n_in, n_out = ta.n_out;
   const uint8_t fl = a.flags ? a.flags[b] : 0;
