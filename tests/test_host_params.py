@@ -144,3 +144,32 @@ def test_croporpad_params_match_reference(name):
     params = transform.make_params(batch)
     assert json.loads(json.dumps(params)) == history[-1]["params"]
     assert history[-1]["name"] == "CropOrPad"
+
+
+@pytest.mark.parametrize("name", ["compose_config2_b2", "compose_full_b2", "compose_full_b1_48"])
+def test_streaming_plan_samples_like_sequential_application(name):
+    """Compose._plan (used when a host batch is streamed in slices) draws gates and params
+    for the whole batch up front: same RNG order, same params as the reference's history."""
+    case, images, history, _, _ = load_golden(name)
+    batch = product_batch(images)
+    transform = make_product_transform(case["transform"])
+    torch.manual_seed(case["seed"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = transform._plan(batch)
+    mine = [{"name": type(t).__name__, "params": p} for _, applied in plan for t, p in applied]
+    assert json.loads(json.dumps(mine)) == history
+    # and slicing the planned params row-wise is what unbatching the history would give
+    from torchio_b200.params import slice_params
+
+    b = batch.batch_size
+    for _, applied in plan:
+        for _, params in applied:
+            part = slice_params(params, 0, 1)
+            if "_batched_keys" in params:
+                assert part["_batch_size"] == 1
+                for key in params["_batched_keys"]:
+                    assert part[key] == params[key][0:1]
+            else:
+                assert part is params
+    assert b >= 1
