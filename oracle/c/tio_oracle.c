@@ -413,3 +413,67 @@ int orc_gamma(const float* src, float* dst, int B, int64_t per_elem, const float
     }
   return 0;
 }
+
+/* ---- widened rows: index-remap neighbours and patch extraction -----------------
+ * Scalar restatements with the signatures of tio_remap / tio_crop_patches
+ * (include/tio_b200.h), host pointers.  torch.flip (spatial/flip.py:233-263), the crop
+ * slice (crop.py:84-101) and F.pad's constant / replicate / reflect / circular modes
+ * (_padding.py:73-104) are one mapping out[o] = in[f(m(o - off))] per spatial axis;
+ * PatchSampler._extract_patch (data/sampler.py:54-67) is a sub-block copy. */
+
+static int remap_index(int s, int n, int mode, int* outside) {
+  if (s >= 0 && s < n) return s;
+  if (mode == 1) return s < 0 ? 0 : n - 1;                 /* replicate */
+  if (mode == 2) {                                         /* reflect (edge not repeated) */
+    if (n == 1) return 0;
+    int period = 2 * (n - 1);
+    int r = s % period;
+    if (r < 0) r += period;
+    return r < n ? r : period - r;
+  }
+  if (mode == 3) { int r = s % n; return r < 0 ? r + n : r; } /* circular */
+  *outside = 1;                                            /* constant */
+  return 0;
+}
+
+int orc_remap(const void* src, void* dst, int elem_bytes, int B, int C, int I, int J, int K,
+              int OI, int OJ, int OK, int off_i, int off_j, int off_k, int mode,
+              const void* fill, const uint8_t* flip) {
+  const char* s = (const char*)src;
+  char* d = (char*)dst;
+  for (int b = 0; b < B; ++b) {
+    const uint8_t fl = flip ? flip[b] : 0;
+    for (int c = 0; c < C; ++c)
+      for (int oi = 0; oi < OI; ++oi)
+        for (int oj = 0; oj < OJ; ++oj)
+          for (int ok = 0; ok < OK; ++ok) {
+            int outside = 0;
+            int si = remap_index(oi - off_i, I, mode, &outside);
+            int sj = remap_index(oj - off_j, J, mode, &outside);
+            int sk = remap_index(ok - off_k, K, mode, &outside);
+            if (fl & 1) si = I - 1 - si;
+            if (fl & 2) sj = J - 1 - sj;
+            if (fl & 4) sk = K - 1 - sk;
+            int64_t o = ((((int64_t)b * C + c) * OI + oi) * OJ + oj) * OK + ok;
+            int64_t i = ((((int64_t)b * C + c) * I + si) * J + sj) * K + sk;
+            if (outside) memcpy(d + o * elem_bytes, fill, (size_t)elem_bytes);
+            else memcpy(d + o * elem_bytes, s + i * elem_bytes, (size_t)elem_bytes);
+          }
+  }
+  return 0;
+}
+
+int orc_crop_patches(const void* src, void* dst, int elem_bytes, int C, int I, int J, int K,
+                     int n, const int32_t* corners, int pi, int pj, int pk) {
+  const char* s = (const char*)src;
+  char* d = (char*)dst;
+  for (int p = 0; p < n; ++p)
+    for (int c = 0; c < C; ++c)
+      for (int i = 0; i < pi; ++i)
+        for (int j = 0; j < pj; ++j) {
+          int64_t o = ((((int64_t)p * C + c) * pi + i) * pj + j) * pk;
+          int64_t q = (((int64_t)c * I + corners[3 * p] + i) * J + corners[3 * p + 1] + j) * K + corners[3 * p + 2];
+          memcpy(d + o * elem_bytes, s + q * elem_bytes, (size_t)pk * elem_bytes);
+        }
+  return 0;
+}

@@ -307,9 +307,72 @@ def gamma(images, params, invert=False):
         img["data"] = out
 
 
+# ---- widened rows: Flip / Crop / Pad through orc_remap, patches through orc_crop_patches --
+
+_PAD_MODES = {"constant": 0, "replicate": 1, "reflect": 2, "circular": 3}
+
+
+def remap(data, out_shape, offsets, mode="constant", fill=0, flip_bits=None):
+    data = data.contiguous()
+    b, c, i, j, k = data.shape
+    out = torch.empty((b, c, *out_shape), dtype=data.dtype)
+    fill_t = torch.tensor([fill]).to(data.dtype)  # F.pad casts the value to the tensor's dtype
+    flip_t = None if flip_bits is None else torch.as_tensor(np.asarray(flip_bits, dtype=np.uint8))
+    rc = lib().orc_remap(_p(data), _p(out), data.element_size(), b, c, i, j, k, *[int(v) for v in out_shape],
+                         int(offsets[0]), int(offsets[1]), int(offsets[2]), _PAD_MODES[mode], _p(fill_t),
+                         _p(flip_t))
+    assert rc == 0
+    return out
+
+
+def _shift_origin(img, voxels):
+    shift = np.asarray(voxels, dtype=np.float64)
+    for a in img["affines"]:
+        a[:3, 3] += a[:3, :3] @ shift
+
+
+def flip(images, params):
+    axes = params["axes"]
+    for img in images.values():
+        b = img["data"].shape[0]
+        per = axes if "_batched_keys" in params else [axes] * b
+        bits = [sum(1 << int(a) for a in set(ax)) for ax in per]
+        if any(bits):
+            img["data"] = remap(img["data"], img["data"].shape[2:], (0, 0, 0), flip_bits=bits)
+
+
+def crop(images, params):
+    i0, i1, j0, j1, k0, k1 = params["cropping"]
+    for img in images.values():
+        si, sj, sk = img["data"].shape[-3:]
+        img["data"] = remap(img["data"], (si - i0 - i1, sj - j0 - j1, sk - k0 - k1), (-i0, -j0, -k0))
+        _shift_origin(img, (i0, j0, k0))
+
+
+def pad(images, params):
+    i0, i1, j0, j1, k0, k1 = params["padding"]
+    for img in images.values():
+        si, sj, sk = img["data"].shape[-3:]
+        img["data"] = remap(img["data"], (si + i0 + i1, sj + j0 + j1, sk + k0 + k1), (i0, j0, k0),
+                            mode=params["padding_mode"], fill=params["fill"])
+        _shift_origin(img, (-i0, -j0, -k0))
+
+
+def crop_patches(volume, corners, size):
+    volume = volume.contiguous()
+    c, i, j, k = volume.shape
+    corners_t = torch.as_tensor(np.asarray(corners, dtype=np.int32).reshape(-1, 3)).contiguous()
+    out = torch.empty((corners_t.shape[0], c, *size), dtype=volume.dtype)
+    rc = lib().orc_crop_patches(_p(volume), _p(out), volume.element_size(), c, i, j, k, corners_t.shape[0],
+                                _p(corners_t), *[int(v) for v in size])
+    assert rc == 0
+    return out
+
+
 _APPLY = {
     "Spatial": spatial, "Affine": spatial, "ElasticDeformation": spatial,
     "BiasField": bias_field, "Blur": blur, "Noise": noise, "Gamma": gamma,
+    "Flip": flip, "Crop": crop, "Pad": pad,
 }
 
 

@@ -11,14 +11,14 @@ import copy
 import pytest
 import torch
 
-from golden_cases import CASES
+from golden_cases import CASES, NEIGHBOUR_CASES
 from oracle import c_port
 from util import load_golden, report
 
 TOL = {"Noise": 5e-6}
 
 
-@pytest.mark.parametrize("name", [c["name"] for c in CASES])
+@pytest.mark.parametrize("name", [c["name"] for c in CASES + NEIGHBOUR_CASES])
 def test_c_oracle_matches_reference_golden(name):
     _, images, history, expected, _ = load_golden(name)
     out = c_port.replay(copy.deepcopy(images), history)
@@ -44,3 +44,13 @@ def test_c_mt19937_randn_matches_torch():
         ref2 = torch.randn(64, generator=g)
         z2, _ = c_port.randn_mt19937(seed, used, 64)
         assert (z2 - ref2).abs().max() <= 4e-6
+
+
+def test_c_crop_patches_equals_slicing():
+    g = torch.Generator().manual_seed(2)
+    for dtype in (torch.uint8, torch.int16, torch.float32, torch.int64):
+        vol = (torch.rand((2, 9, 10, 11), generator=g) * 50).to(dtype)
+        corners = [[0, 0, 0], [2, 3, 4], [5, 4, 3]]
+        got = c_port.crop_patches(vol, corners, (4, 6, 7))
+        for row, (i, j, k) in enumerate(corners):
+            assert torch.equal(got[row], vol[:, i:i + 4, j:j + 6, k:k + 7])
