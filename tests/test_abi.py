@@ -42,3 +42,25 @@ def test_bad_arguments_fail_loudly_without_touching_the_gpu():
         sp = (ctypes.c_float * 3)(1, 1, 1)
         _native.call("tio_resample", p, p, 0, 1, 1, 2, 2, 2, 2, 2, 2, p, None, None, 0, 0, 0,
                      ctypes.addressof(sp), ctypes.addressof(sp), 1, 1, None, 0, None, 0, None)
+
+
+def test_widened_entry_points_validate_before_launching():
+    """tio_upload / tio_crop_patches / tio_remap: non-zero return + message, no CUDA call."""
+    import pytest
+
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.addressof(buf)
+    with pytest.raises(RuntimeError, match="null"):
+        _native.call("tio_upload", None, None, 16, None)
+    with pytest.raises(RuntimeError, match="does not fit"):
+        _native.call("tio_crop_patches", p, p + 128, 4, 1, 4, 4, 4, 1, p, 8, 2, 2, None)
+    with pytest.raises(RuntimeError, match="element size"):
+        _native.call("tio_crop_patches", p, p + 128, 3, 1, 4, 4, 4, 1, p, 2, 2, 2, None)
+    with pytest.raises(RuntimeError, match="aliased"):
+        _native.call("tio_remap", p, p, 4, 1, 1, 2, 2, 2, 2, 2, 2, 0, 0, 0, 0, None, None, None)
+    with pytest.raises(RuntimeError, match="mode"):
+        _native.call("tio_remap", p, p + 128, 4, 1, 1, 2, 2, 2, 2, 2, 2, 0, 0, 0, 7, None, None, None)
+    with pytest.raises(RuntimeError, match="reflect"):
+        _native.call("tio_remap", p, p + 128, 4, 1, 1, 2, 2, 2, 6, 2, 2, 2, 0, 0, 2, None, None, None)
+    # an empty upload is a no-op, not an error
+    assert _native.lib().tio_upload(p, p + 128, 0, None) == 0
