@@ -54,3 +54,34 @@ def test_c_crop_patches_equals_slicing():
         got = c_port.crop_patches(vol, corners, (4, 6, 7))
         for row, (i, j, k) in enumerate(corners):
             assert torch.equal(got[row], vol[:, i:i + 4, j:j + 6, k:k + 7])
+
+
+def test_c_remap_equals_torch_pad_flip_crop_on_random_cases():
+    """orc_remap against F.pad / torch.flip / slicing for random offsets, modes, dtypes."""
+    import numpy as np
+
+    rng = np.random.default_rng(4)
+    g = torch.Generator().manual_seed(4)
+    for trial in range(40):
+        dtype = [torch.float32, torch.int16, torch.uint8, torch.float64][trial % 4]
+        shape = tuple(int(v) for v in rng.integers(3, 9, 3))
+        x = (torch.rand((2, 2, *shape), generator=g) * 90).to(dtype)
+        mode = ["constant", "replicate", "reflect", "circular"][int(rng.integers(0, 4))]
+        limit = [min(s - 1, 3) if mode in ("reflect", "circular") else 3 for s in shape]
+        pad = [int(rng.integers(0, limit[a] + 1)) for a in range(3) for _ in range(2)]
+        if mode != "constant" and dtype not in (torch.float32, torch.float64):
+            continue  # F.pad's non-constant modes are float-only on the CPU; covered for floats
+        kw = {"value": 7} if mode == "constant" else {}
+        want = torch.nn.functional.pad(x, (pad[4], pad[5], pad[2], pad[3], pad[0], pad[1]), mode=mode, **kw)
+        out_shape = tuple(shape[a] + pad[2 * a] + pad[2 * a + 1] for a in range(3))
+        got = c_port.remap(x, out_shape, (pad[0], pad[2], pad[4]), mode=mode, fill=7)
+        assert torch.equal(got, want), (trial, mode, pad)
+        # crop + per-element flips in one remap: the reversal acts on the source volume,
+        # i.e. out = flip(source)[window]
+        bits = [int(rng.integers(0, 8)) for _ in range(2)]
+        back = c_port.remap(got, shape, (-pad[0], -pad[2], -pad[4]), flip_bits=bits)
+        for b in range(2):
+            dims = [a - 3 for a in range(3) if bits[b] >> a & 1]
+            flipped = torch.flip(got[b], dims) if dims else got[b]
+            ref = flipped[:, pad[0]:pad[0] + shape[0], pad[2]:pad[2] + shape[1], pad[4]:pad[4] + shape[2]]
+            assert torch.equal(back[b], ref), (trial, bits)
