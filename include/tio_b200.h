@@ -43,6 +43,11 @@ enum tio_dtype {
 };
 
 enum tio_interp { TIO_NEAREST = 0, TIO_LINEAR = 1 };
+/* OR into `mode`: keep the reference's fp32 rounding sequence of the sampling coordinates on
+ * every tile.  Without it, fp32 trilinear tiles whose taps all lie inside the volume evaluate the
+ * same mapping with one fma per axis (differs from the reference's own coordinate noise by
+ * <= ~2e-5 voxel); label maps, border tiles and fill decisions are always exact. */
+#define TIO_EXACT_COORDS 0x100
 
 /* per-element flag bits for tio_resample */
 #define TIO_FLAG_PASSTHROUGH 1u /* copy the row bit-exactly (spatial.py:1101-1106) */

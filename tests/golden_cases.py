@@ -228,7 +228,36 @@ CALL_CASES = [
          transform=("CropOrPad", {"target_shape": (12, 8, None), "only_pad": True, "fill": 2.5})),
 ]
 
-CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES}
+# ---- BASELINE.json's own volume size: 256^3 (configs[1] and configs[2], two elements) ----------
+# The reference's full outputs are too large to commit (64 MiB per volume): the fixture keeps
+# a strided lattice of every output, two dense blocks (a corner with padding/fill, the centre),
+# and SHA-256 of the full label maps (bit-exact by construction).
+_P_AFF = ("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)})
+FULL_CASES = [
+    dict(name="full256_config2_b2", seed=1234, shape=(256, 256, 256), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=[_P_AFF, ("ElasticDeformation", {})]),
+    dict(name="full256_config3_b2", seed=1234, shape=(256, 256, 256), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=[_P_AFF, ("ElasticDeformation", {}), ("BiasField", {}), ("Blur", {"std": (0.0, 2.0)}),
+                    ("Noise", {"std": (0.0, 0.25)}), ("Gamma", {"log_gamma": (-0.3, 0.3)})]),
+]
+FULL_STRIDE, FULL_OFFSET, FULL_BLOCK = 9, (3, 5, 2), 24
+
+
+def full_views(t):
+    """The parts of a (B,C,256,256,256) output the full-size fixture stores."""
+    oi, oj, ok = FULL_OFFSET
+    n = t.shape[-1]
+    c0 = (n - FULL_BLOCK) // 2
+    return {
+        "lattice": t[..., oi::FULL_STRIDE, oj::FULL_STRIDE, ok::FULL_STRIDE],
+        "corner": t[..., :FULL_BLOCK, n - FULL_BLOCK:, :FULL_BLOCK],
+        "centre": t[..., c0:c0 + FULL_BLOCK, c0:c0 + FULL_BLOCK, c0:c0 + FULL_BLOCK],
+    }
+
+
+CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES + FULL_CASES}
 
 
 # ---- patch path (SURVEY §8 f-2): UniformSampler / Queue / SubjectsLoader -------------

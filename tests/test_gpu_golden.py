@@ -20,8 +20,12 @@ TOL_RANGE = 1e-4
 SPATIAL = {"Affine", "ElasticDeformation", "Spatial"}
 
 
+# fast coordinates: the reference's own coordinate noise (<= ~2e-5 voxel) times the local gradient
+TOL_FAST_VS_ORACLE = 1e-4
+
+
 @pytest.mark.parametrize("name", [c["name"] for c in CASES])
-def test_cuda_matches_reference_golden(name):
+def test_cuda_matches_reference_golden(name, coords):
     from oracle import c_port
 
     _, images, history, expected, expected_aff = load_golden(name)
@@ -41,10 +45,13 @@ def test_cuda_matches_reference_golden(name):
         ro = report(got, oracle[n]["data"])
         if only_spatial and images[n]["kind"] == "label":
             assert ro["n_mismatch"] == 0, (n, ro)  # same coordinates, same rounding
-        elif only_spatial:  # same coordinates; taps blended with FMA lerps (<= 1 ulp)
+        elif only_spatial and coords == "exact":  # same coordinates; taps blended with FMA lerps (<= 1 ulp)
             assert ro["max_abs_over_range"] <= 3e-7, (n, ro)
-        else:
+        elif coords == "exact":
             assert ro["max_abs_over_range"] <= 2e-6, (n, ro)
+        else:
+            assert ro["max_abs_over_range"] <= TOL_FAST_VS_ORACLE and ro["frac_gt_1e-4_range"] == 0.0, (n, ro)
+        assert r["frac_gt_1e-4_range"] == 0.0 or images[n]["kind"] == "label", (n, r)
         for b, a in enumerate(out.images[n].affines):
             assert abs(a.numpy() - expected_aff[n][b]).max() < 1e-12
 

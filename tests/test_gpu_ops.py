@@ -33,7 +33,7 @@ def _random_matrix(rng, shape, big=False):
     return m.astype(np.float32)[:3].reshape(12)
 
 
-def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill, box_hint=-1):
+def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill, box_hint=-1, exact_coords=True):
     from torchio_b200 import ops
 
     c_port = _orc()
@@ -48,6 +48,7 @@ def _run_both(data, mat, cp, flags, sp_in, sp_out, affine_first, mode, fill, box
         data.to(dev), mat_t.to(dev), None if cp_t is None else cp_t.to(dev),
         None if fl_t is None else fl_t.to(dev), sp_in, sp_out, affine_first=affine_first,
         mode=mode, fill=None if fill_t is None else fill_t.to(dev), box_hint=box_hint,
+        exact_coords=exact_coords,
     ).cpu()
     want = torch.empty_like(data)
     ni, nj, nk = (0, 0, 0) if cp is None else cp.shape[1:4]
@@ -86,11 +87,13 @@ def test_resample_bit_exact_vs_c_oracle(shape, mode, elastic):
                                   affine_first, mode, fill)
             assert torch.equal(got, want), int((got != want).sum())
             if mode == 1:
-                # TMA tile path: same coordinates and fill decisions, FMA tap blending
-                for hint in (0, 20, 22, 28, 32):
+                # TMA tile paths: exact = same coordinates, FMA tap blending; fast = one-fma
+                # coordinates where no tap leaves the volume.  Same fill decisions either way.
+                for hint, exact in ((0, True), (20, True), (22, True), (28, True), (32, True),
+                                    (0, False), (20, False), (22, False), (24, False), (28, False), (32, False)):
                     fast, _ = _run_both(data, mat, cp, flags, (0.8, 1.1, 2.0), (0.8, 1.1, 2.0),
-                                        affine_first, mode, fill, box_hint=hint)
-                    assert float((fast - want).abs().max()) <= 1e-6
+                                        affine_first, mode, fill, box_hint=hint, exact_coords=exact)
+                    assert float((fast - want).abs().max()) <= (1e-6 if exact else 1e-4), (hint, exact)
                     if fill is not None:
                         for ch in range(c):
                             filled_fast = fast[:, ch] == float(fill[ch])
@@ -338,7 +341,7 @@ def test_noise_exact_mode_uses_device_stream_and_matches_reference():
             assert float((out.images[k].data.cpu() - ref[k]["data"]).abs().max()) <= 4e-6
 
 
-def test_streamed_host_batch_equals_one_shot_rows():
+def test_streamed_host_batch_equals_one_shot_rows(coords):
     """Compose streams a host-resident batch through the device in slices of the batch
     axis (copy in / kernels / copy out overlapped); every row, affine and the history
     must equal the one-shot path (tile-vs-general resample paths differ <= 1e-6)."""
@@ -376,7 +379,9 @@ def test_streamed_host_batch_equals_one_shot_rows():
     one, streamed = outs
     assert streamed.images["t1"].data.device.type == "cpu"
     rng = float(one.images["t1"].data.max() - one.images["t1"].data.min())
-    assert float((one.images["t1"].data - streamed.images["t1"].data).abs().max()) <= 3e-6 * rng
+    # (fast coordinates are box relative, and the box edge follows the slice's matrices)
+    tol = 3e-6 if coords == "exact" else 3e-5
+    assert float((one.images["t1"].data - streamed.images["t1"].data).abs().max()) <= tol * rng
     assert torch.equal(one.images["seg"].data, streamed.images["seg"].data)
     for a, b in zip(one.images["t1"].affines, streamed.images["t1"].affines):
         assert a == b

@@ -73,7 +73,7 @@ def test_full_pipeline_gated_rows_are_bit_exact_and_labels_stay_in_set():
     assert torch.isfinite(y).all()
 
 
-def test_trilinear_resample_is_linear_and_tile_path_equals_general_path():
+def test_trilinear_resample_is_linear_and_tile_path_equals_general_path(coords):
     from torchio_b200 import ops
 
     rng = np.random.default_rng(5)
@@ -94,12 +94,13 @@ def test_trilinear_resample_is_linear_and_tile_path_equals_general_path():
     rxy = ops.resample(0.3 * x - 1.7 * y, mat, cp, flags, one, one, **kw)
     assert float((rxy - (0.3 * rx - 1.7 * ry)).abs().max()) <= 5e-6
     general = ops.resample(x, mat, cp, flags, one, one, box_hint=-1, **kw)
-    assert float((rx - general).abs().max()) <= 1e-6
+    tol = 1e-6 if coords == "exact" else 1e-4  # fast: the reference's coordinate noise x white-noise gradients (measured 6.2e-5)
+    assert float((rx - general).abs().max()) <= tol
     fill = torch.tensor([-3.0]).cuda()
     f_fast = ops.resample(x, mat, cp, flags, one, one, affine_first=True, mode=ops.LINEAR, fill=fill)
     f_gen = ops.resample(x, mat, cp, flags, one, one, affine_first=True, mode=ops.LINEAR, fill=fill, box_hint=-1)
     assert torch.equal(f_fast == -3.0, f_gen == -3.0)  # identical fill decisions
-    assert float((f_fast - f_gen).abs().max()) <= 1e-6
+    assert float((f_fast - f_gen).abs().max()) <= tol
 
 
 def test_resample_block_matches_c_oracle_at_full_size():

@@ -1,0 +1,158 @@
+"""K1 development harness (GPU): fast (one-fma coordinates) vs exact tile kernel vs general gather.
+
+    python tools/k1_dev.py [check] [time] [B=32]
+
+check: 256^3, random affines (+-10 deg, 0.9-1.1, translation) and elastic grids, with and without a
+fill value: fast path vs exact tile path (tolerance + identical fill decisions + identical border
+voxels) and vs the general kernel.  time: CUDA-event timing of both paths at batch B.
+"""
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from torchio_b200 import ops  # noqa: E402
+
+S = 256
+
+
+def rot(d):
+    x, y, z = np.radians(d)
+    rx = np.array([[1, 0, 0], [0, np.cos(x), -np.sin(x)], [0, np.sin(x), np.cos(x)]])
+    ry = np.array([[np.cos(y), 0, np.sin(y)], [0, 1, 0], [-np.sin(y), 0, np.cos(y)]])
+    rz = np.array([[np.cos(z), -np.sin(z), 0], [np.sin(z), np.cos(z), 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def matrices(b, rng, translate=3.0):
+    out = np.zeros((b, 12), np.float32)
+    c = np.full(3, (S - 1) / 2)
+    for t in range(b):
+        fwd = rot(rng.uniform(-10, 10, 3)) @ np.diag(rng.uniform(0.9, 1.1, 3))
+        m = np.eye(4)
+        m[:3, :3] = fwd
+        m[:3, 3] = c - fwd @ c + rng.uniform(-translate, translate, 3)
+        out[t] = np.linalg.inv(m)[:3].astype(np.float32).reshape(12)
+    return torch.tensor(out).cuda()
+
+
+def control(b, rng, amp=7.5):
+    cp = rng.uniform(-amp, amp, (b, 7, 7, 7, 3)).astype(np.float32)
+    for ax in (1, 2, 3):  # two locked border shells (spatial.py:2241-2266)
+        idx = [slice(None)] * 5
+        for border in (0, 1, -1, -2):
+            idx[ax] = border
+            cp[tuple(idx)] = 0
+            idx[ax] = slice(None)
+    return torch.tensor(cp).cuda()
+
+
+def stats(a, b):
+    d = (a - b).abs()
+    return dict(max=float(d.max()), frac_gt_1e4=float((d > 1e-4).float().mean()), mean=float(d.mean()))
+
+
+def check():
+    rng = np.random.default_rng(11)
+    b = 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((b, 1, S, S, S), generator=g).cuda()
+    one = (1.0, 1.0, 1.0)
+    ident = torch.tensor(np.tile(np.eye(4, dtype=np.float32)[:3].reshape(1, 12), (b, 1))).cuda()
+    el = torch.full((b,), 2, dtype=torch.uint8).cuda()
+    cases = {
+        "affine": (matrices(b, rng), None, None, True, one, one),
+        "elastic": (ident, control(b, rng), el, True, one, one),
+        "affine+elastic": (matrices(b, rng), control(b, rng), el, True, one, one),
+        "elastic-first": (matrices(b, rng), control(b, rng), el, False, one, one),
+        "spacing": (matrices(b, rng), control(b, rng), el, True, (1.0, 0.8, 1.25), (1.0, 0.8, 1.25)),
+        "spacing-elastic-first": (matrices(b, rng), control(b, rng), el, False, (1.0, 0.8, 1.25), (1.1, 0.9, 1.0)),
+    }
+    ok = True
+    for name, (mat, cp, flags, af, si, so) in cases.items():
+        for fill in (None, torch.tensor([-3.0]).cuda()):
+            for hint in (24, 22):
+                kw = dict(affine_first=af, mode=ops.LINEAR, fill=fill)
+                fast = ops.resample(x, mat, cp, flags, si, so, exact_coords=False, box_hint=hint, **kw)
+                exact = ops.resample(x, mat, cp, flags, si, so, exact_coords=True, box_hint=hint, **kw)
+                gen = ops.resample(x, mat, cp, flags, si, so, box_hint=-1, **kw)
+                s1, s2 = stats(fast, exact), stats(fast, gen)
+                line = f"{name:24s} fill={'y' if fill is not None else 'n'} box={hint} fast-exact {s1} fast-general max {s2['max']:.2e}"
+                if fill is not None:
+                    same = bool(torch.equal(fast == -3.0, gen == -3.0))
+                    line += f" fill-decisions-equal={same}"
+                    ok &= same
+                # voxels on the outer shell of the output were computed by the exact column or border logic
+                ok &= s1["max"] <= 1e-4 and s2["max"] <= 1e-4
+                print(line, flush=True)
+    print("CHECK", "OK" if ok else "FAILED")
+    return ok
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def time_all(b):
+    rng = np.random.default_rng(3)
+    x = torch.rand((b, 1, S, S, S), device="cuda")
+    y = torch.empty_like(x)  # second buffer larger than L2 keeps the runs cold
+    one = (1.0, 1.0, 1.0)
+    ident = torch.tensor(np.tile(np.eye(4, dtype=np.float32)[:3].reshape(1, 12), (b, 1))).cuda()
+    el = torch.full((b,), 2, dtype=torch.uint8).cuda()
+    mats, cp = matrices(b, rng, 0.0), control(b, rng)
+    fill = ops.min_sample0(x)
+    gb = 8.0 * b * S**3 / 1e9
+    for name, (mat, cps, flags) in {"affine": (mats, None, None), "elastic": (ident, cp, el)}.items():
+        for hint in (24, 22):
+            for exact in (True, False):
+                ms = timeit(lambda: ops.resample(x, mat, cps, flags, one, one, affine_first=True, mode=ops.LINEAR,
+                                                 fill=fill, box_hint=hint, exact_coords=exact))
+                print(f"TIME {name:8s} box={hint} {'exact' if exact else 'fast '} {ms:.3f} ms  "
+                      f"{gb / ms:.0f} GB/s  lk={os.environ.get('TIO_B200_K1_LK', '16')}", flush=True)
+    del y
+
+
+if __name__ == "__main__":
+    args = sys.argv[1:]
+    b = 32
+    for a in args:
+        if a.startswith("B="):
+            b = int(a[2:])
+    if "check" in args or not args:
+        check()
+    if "time" in args or not args:
+        time_all(b)
+
+
+def ncu_mode(b):
+    """Two launches of each path for an `ncu -k regex:resample_ --launch-skip ...` capture."""
+    rng = np.random.default_rng(3)
+    x = torch.rand((b, 1, S, S, S), device="cuda")
+    one = (1.0, 1.0, 1.0)
+    ident = torch.tensor(np.tile(np.eye(4, dtype=np.float32)[:3].reshape(1, 12), (b, 1))).cuda()
+    el = torch.full((b,), 2, dtype=torch.uint8).cuda()
+    mats, cp = matrices(b, rng, 0.0), control(b, rng)
+    fill = ops.min_sample0(x)
+    hint = int(os.environ.get("K1_BOX", "24"))
+    for _ in range(2):
+        for mat, cps, flags in ((mats, None, None), (ident, cp, el)):
+            ops.resample(x, mat, cps, flags, one, one, affine_first=True, mode=ops.LINEAR, fill=fill,
+                         box_hint=hint, exact_coords=False)
+    torch.cuda.synchronize()
+
+
+if "ncu" in sys.argv[1:]:
+    ncu_mode(int(os.environ.get("K1_B", "32")))

@@ -10,6 +10,7 @@ of ``include/tio_b200.h``; see DESIGN.md and INTEGRATION.md.
 
 from .data import (AffineMatrix, Image, ImagesBatch, LabelMap, ScalarImage, StudiesBatch,
                    Subject, SubjectsBatch)
+from .ops import exact_coords_default, set_exact_coords
 from .params import Choice
 from .patches import (GridSampler, ImagesLoader, LabelSampler, PatchLocation, PatchSampler, Queue,
                       StudiesLoader, SubjectsLoader, UniformSampler, WeightedSampler, collate_images, collate_studies,
@@ -27,6 +28,6 @@ __all__ = [
     "LabelMap", "LabelSampler", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
     "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
     "SubjectsLoader", "Transform", "UniformSampler", "WeightedSampler", "apply_inverse_transform", "collate_images",
-    "collate_studies", "collate_subjects", "execution_device", "get_inverse_transform",
-    "set_execution_device",
+    "collate_studies", "collate_subjects", "exact_coords_default", "execution_device", "get_inverse_transform",
+    "set_exact_coords", "set_execution_device",
 ]

@@ -17,9 +17,9 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-SOURCES = ["error.cu", "resample.cu", "resample_tile.cu", "intensity.cu", "fused_intensity.cu",
+SOURCES = ["error.cu", "resample.cu", "resample_tile.cu", "resample_fast.cu", "intensity.cu", "fused_intensity.cu",
            "mt19937_jump.cpp", "mt19937.cu", "patches.cu"]
-HEADERS = [HERE / "common.cuh", HERE / "intensity_common.cuh", HERE / "resample_common.cuh", HERE / "tma.cuh",
+HEADERS = [HERE / "common.cuh", HERE / "intensity_common.cuh", HERE / "resample_common.cuh", HERE / "resample_tile.cuh", HERE / "tma.cuh",
            ROOT / "include" / "tio_b200.h"]
 OBJ = HERE / "_obj"
 OUT = HERE / "libtio_b200.so"

@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ src,
   }
 }
 
-int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, int box_hint, void* workspace,
-                         size_t workspace_bytes, cudaStream_t st);
+int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_coords, int box_hint,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK);
 
 }  // namespace tio
@@ -157,6 +157,8 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   TIO_CHECK_ARG(src != dst, "tio_resample: src and dst must not alias");
   TIO_CHECK_ARG(B > 0 && C > 0 && I > 0 && J > 0 && K > 0 && OI > 0 && OJ > 0 && OK > 0,
                 "tio_resample: non-positive shape");
+  const bool exact_coords = (mode & TIO_EXACT_COORDS) != 0;
+  mode &= ~TIO_EXACT_COORDS;
   TIO_CHECK_ARG(mode == TIO_NEAREST || mode == TIO_LINEAR, "tio_resample: bad mode %d", mode);
   TIO_CHECK_ARG(spacing_in && spacing_out, "tio_resample: null spacing");
   TIO_CHECK_ARG(!cp || (ni >= 2 && nj >= 2 && nk >= 2), "tio_resample: control grid < 2 per axis");
@@ -181,7 +183,7 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   a.cp_in_smem = cp && ((size_t)ni * nj * nk * 12 <= 96 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
   if (box_hint >= 0) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
-    const int rc = launch_resample_tile(a, dtype, mode, box_hint, workspace, workspace_bytes, st);
+    const int rc = launch_resample_tile(a, dtype, mode, exact_coords, box_hint, workspace, workspace_bytes, st);
     if (rc == 0) {
       TIO_CHECK_LAUNCH();
       return 0;

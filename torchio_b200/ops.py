@@ -9,6 +9,7 @@ caller's current CUDA stream on the tensor's device.  No CPU fallback.
 
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
@@ -148,10 +149,26 @@ def upload(device: torch.device, *arrays):
     return out
 
 
+EXACT_COORDS = 0x100  # TIO_EXACT_COORDS
+_exact_default = os.environ.get("TIO_B200_EXACT_COORDS", "0") not in ("", "0")
+
+
+def set_exact_coords(enabled: bool) -> bool:
+    """Process-wide default of ``resample(exact_coords=None)``; returns the previous value.
+    Also settable with ``TIO_B200_EXACT_COORDS=1`` before import."""
+    global _exact_default
+    previous, _exact_default = _exact_default, bool(enabled)
+    return previous
+
+
+def exact_coords_default() -> bool:
+    return _exact_default
+
+
 def resample(
     src: Tensor, mat: Tensor, cp: Tensor | None, flags: Tensor | None,
     spacing_in, spacing_out, *, affine_first: bool, mode: int,
-    fill: Tensor | None, out_shape=None, box_hint: int = 0,
+    fill: Tensor | None, out_shape=None, box_hint: int = 0, exact_coords: bool | None = None,
 ) -> Tensor:
     """K1.  Replaces _build_sampling_grid + _sample_batch[_per_sample]
     (spatial/spatial.py:1504-1579,1651-1857).
@@ -159,6 +176,12 @@ def resample(
     src (B,C,I,J,K) fp32 or integer label dtype; mat (B,12) fp32 cuda;
     cp (B,ni,nj,nk,3) fp32 cuda or None; flags (B,) uint8 cuda or None;
     fill (C,) fp32 cuda or None (= no mask step).
+
+    exact_coords: keep the reference's fp32 rounding sequence of the sampling coordinates on
+    every voxel (TIO_EXACT_COORDS).  Default (None -> ``exact_coords_default()``): fp32
+    trilinear voxels whose taps all lie inside the volume use one fma per axis, which differs
+    from the reference by its own coordinate noise (<= ~2e-5 voxel); label maps, padding and
+    fill decisions are exact either way.
     """
     _require_cuda(src, "resample")
     if src.dtype not in DTYPE_CODES:
@@ -182,7 +205,8 @@ def resample(
         _native.call(
             "tio_resample", _ptr(src), _ptr(dst), DTYPE_CODES[src.dtype],
             b, c, i, j, k, oi, oj, ok, _ptr(mat), _ptr(cp), _ptr(flags), ni, nj, nk,
-            sp_in.ctypes.data, sp_out.ctypes.data, int(bool(affine_first)), int(mode),
+            sp_in.ctypes.data, sp_out.ctypes.data, int(bool(affine_first)),
+            int(mode) | (EXACT_COORDS if (_exact_default if exact_coords is None else exact_coords) else 0),
             _ptr(fill), int(box_hint), _ptr(workspace), ws_bytes, _stream(src),
         )
     _count(2 if workspace is not None else 1)
