@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: skip the nvidia-smi sampler")
+    ap.add_argument("--no-numa", action="store_true", help="diagnostic: do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the configs[3] / configs[4] / gpu_baseline legs after the main timed region")
     ap.add_argument("--labels", action="store_true",
                     help="configs[3] shape: add an int16 LabelMap (nearest-neighbour resample) to every volume")
     return ap.parse_args()
@@ -157,9 +160,13 @@ def run_b200(args, rank, world, local_rank):
     import torchio_b200 as tio
     from torchio_b200 import ops
 
+    from torchio_b200 import parallel
+
     os.environ["TIO_B200_NOISE"] = args.noise
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # this rank's threads and (first-touch) pinned staging buffers next to its GPU
+    numa = None if args.no_numa else parallel.bind_to_gpu_numa(local_rank)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         pipeline = tio.Compose(
@@ -257,12 +264,39 @@ def run_b200(args, rank, world, local_rank):
         del res
     ops.resample = raw_resample
 
+    # the one exchange the north-star names: augmented volumes of every rank -> rank 0 (NCCL
+    # send/recv over NVLink), timed on its own and reported beside the augmentation throughput
+    gather = None
     if world > 1:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], device=dev)
+        out = step(resident)
+        counts = [args.batch] * world
+        dest = parallel.gather_buffers(out, counts) if rank == 0 else None
+        for _ in range(2):
+            parallel.gather_batch_to_root(out, counts=counts, out=dest)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            parallel.gather_batch_to_root(out, counts=counts, out=dest)
+        g1.record()
+        barrier()
+        gather = {"ms": g0.elapsed_time(g1) / reps,
+                  "bytes_into_root": (world - 1) * sum(ib.data.numel() * ib.data.element_size()
+                                                       for ib in out.images.values())}
+        del out, dest
+
+    extras = {}
+    if rank == 0 and not args.no_extras and world == 1:
+        extras = extra_legs(args, dev, pipeline_spec, tio, ops)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, gather["ms"]], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
         if e2e:
             e2e["ms"] = float(t[1])
+        gather["ms"] = float(t[2])
     if rank != 0:
         return None
 
@@ -325,9 +359,214 @@ def run_b200(args, rank, world, local_rank):
             "d2h_bytes_per_step": e2e["bytes_out"],
             "ms_per_step": e2e["ms"] / args.steps,
         }
+    if numa is not None:
+        line["config"]["numa"] = numa
+    if gather:
+        gbs = gather["bytes_into_root"] / (gather["ms"] * 1e-3) / 1e9
+        step_ms = ms / args.steps
+        line["gather"] = {
+            "what": "parallel.gather_batch_to_root: every rank's augmented batch -> rank 0, NCCL send/recv",
+            "ms": gather["ms"],
+            "bytes_into_root": gather["bytes_into_root"],
+            "gb_per_s": gbs,
+            "frac_of_900_gbs_root_ingest": gbs / 900.0,
+            "value_with_gather": world * voxels / ((step_ms + gather["ms"]) * 1e-3),
+            "value_without_gather": value,
+        }
+    line.update(extras)
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)
+        line["cpu_baseline"] = cpu_reference(args, steps=3, warmup=1)
     return line
+
+
+def extra_legs(args, dev, pipeline_spec, tio, ops):
+    """Measured after the main region (N = 1): configs[3]'s per-GPU shape (image + int16 label
+    map), configs[4]'s patch path, and the reference's op sequence on CUDA tensors."""
+    out = {}
+    size, batch = args.size, args.batch
+    voxels = batch * size**3
+    # ---- configs[3]: batch of fp32 image + int16 LabelMap, full Compose ----
+    if args.workload == "full" and not args.labels:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pipe = tio.Compose([getattr(tio, n)(**kw) for n, kw in pipeline_spec("full")], copy=False)
+        idx = torch.arange(size)
+        ring = torch.minimum(idx, size - 1 - idx)
+        depth = torch.minimum(torch.minimum(ring[:, None, None], ring[None, :, None]), ring[None, None, :])
+        one = (depth * 5 // max(size // 2, 1)).clamp_(0, 4).to(torch.int16)
+        labels = one[None, None].expand(batch, 1, -1, -1, -1).contiguous().to(dev)
+        images = torch.rand((batch, 1, size, size, size), device=dev)
+        affines = [tio.AffineMatrix() for _ in range(batch)]
+        label_ms = []
+        raw = ops.resample
+
+        def timed(src, *a, **kw):
+            if src.dtype != torch.int16:
+                return raw(src, *a, **kw)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = raw(src, *a, **kw)
+            e.record()
+            label_ms.append((s, e))
+            return r
+
+        ops.resample = timed
+
+        def one_step():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return pipe(tio.SubjectsBatch({
+                    "t1": tio.ImagesBatch(images, list(affines)),
+                    "seg": tio.ImagesBatch(labels, list(affines), image_class=tio.LabelMap)}))
+
+        torch.manual_seed(77)
+        for _ in range(3):
+            one_step()
+        label_ms.clear()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 5
+        t0.record()
+        for _ in range(steps):
+            one_step()
+        t1.record()
+        torch.cuda.synchronize()
+        ops.resample = raw
+        ms = t0.elapsed_time(t1) / steps
+        lab = [s.elapsed_time(e) for s, e in label_ms]
+        lab_avg = sum(lab) / len(lab)
+        peak = 6576.4
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak = float(json.loads(peaks_path.read_text()).get("hbm_gbs", peak))
+        out["config3"] = {
+            "workload": "configs[3] per-GPU shape: batch %d of (1x%d^3 fp32 image + int16 LabelMap, nearest),"
+                        " full Compose, resident" % (batch, size),
+            "ms_per_step": ms,
+            "value": voxels / (ms * 1e-3),
+            "unit": "voxels/s",
+            "label_pass": {
+                "kernel": "resample_tile_kernel<int16, nearest> (%d launches)" % len(lab),
+                "avg_launch_ms": lab_avg,
+                "algorithmic_bytes_per_voxel": 4,
+                "achieved_gb_s": 4 * voxels / (lab_avg * 1e-3) / 1e9,
+                "frac_of_hbm_peak": 4 * voxels / (lab_avg * 1e-3) / 1e9 / peak,
+            },
+        }
+        del labels, images
+        torch.cuda.empty_cache()
+    # ---- configs[4]: Queue(128^3 patches, 8 per volume, max_length 512) -> dummy 3-D UNet forward ----
+    try:
+        out["config4"] = queue_unet_leg(args, dev, tio)
+    except Exception as exc:  # never lose the headline line to an extra
+        out["config4"] = {"error": repr(exc)}
+    # ---- the reference's op sequence on CUDA tensors (the existing Blackwell path) ----
+    if not args.no_cpu_baseline:
+        try:
+            out["gpu_baseline"] = gpu_reference(args, dev)
+        except Exception as exc:
+            out["gpu_baseline"] = {"error": repr(exc)}
+    return out
+
+
+def queue_unet_leg(args, dev, tio):
+    """configs[4] on one GPU: subjects of 1x256^3 -> Compose on the device -> 8 patches of 128^3 per
+    volume into the device patch ring (max_length 512 would be 4 GiB; 64 here) -> batches of 8 ->
+    forward of a small conv3d encoder/decoder.  patches/s, augmentation + extraction + forward."""
+    import torch.nn as nn
+
+    size = args.size
+    n_subjects, per_volume, patch, batch_size, max_length = 16, 8, 128, 8, 64
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pipe = tio.Compose([getattr(tio, n)(**kw) for n, kw in pipeline_spec("full")], copy=False)
+    subjects = []
+    for i in range(n_subjects):
+        g = torch.Generator().manual_seed(2000 + i)
+        subjects.append(tio.Subject(t1=tio.ScalarImage(torch.rand((1, size, size, size), generator=g))))
+    sampler = tio.UniformSampler(patch)
+    queue = tio.Queue(subjects, max_length=max_length, patches_per_volume=per_volume, patch_sampler=sampler,
+                      transform=pipe, num_workers=0, shuffle_subjects=False, shuffle_patches=True, device=dev)
+    loader = tio.SubjectsLoader(queue, batch_size=batch_size)
+    net = nn.Sequential(
+        nn.Conv3d(1, 8, 3, padding=1), nn.ReLU(inplace=True), nn.Conv3d(8, 16, 3, stride=2, padding=1),
+        nn.ReLU(inplace=True), nn.Conv3d(16, 16, 3, padding=1), nn.ReLU(inplace=True),
+        nn.ConvTranspose3d(16, 8, 2, stride=2), nn.ReLU(inplace=True), nn.Conv3d(8, 2, 1),
+    ).to(dev).to(memory_format=torch.channels_last_3d).half()
+    torch.manual_seed(5)
+    n_patches = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for batch in loader:
+            x = batch.images["t1"].data
+            y = net(x.half().contiguous(memory_format=torch.channels_last_3d))
+            n_patches += x.shape[0]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert y.shape[0] > 0
+    return {
+        "workload": "configs[4] on one GPU: Queue(%d subjects of 1x%d^3 on the host, Compose of six on the device,"
+                    " UniformSampler(%d), patches_per_volume=%d, max_length=%d, device ring) ->"
+                    " SubjectsLoader(batch_size=%d) -> conv3d encoder/decoder forward (fp16)"
+                    % (n_subjects, size, patch, per_volume, max_length, batch_size),
+        "patches": n_patches,
+        "seconds": dt,
+        "value": n_patches / dt,
+        "unit": "patches/s",
+        "patch_voxels_per_s": n_patches * patch**3 / dt,
+        "includes": "H2D of each subject, augmentation, patch gather, UNet forward",
+    }
+
+
+def gpu_reference(args, dev):
+    """The reference's op sequence (oracle/torch_port.py = what TorchIO runs) on CUDA tensors of
+    the same B200: the existing Blackwell path the fused kernels are compared with."""
+    import numpy as np
+
+    import torchio_b200 as tio
+    from oracle import torch_port
+
+    b, size = 2, args.size
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        transforms = [getattr(tio, n)(**kw) for n, kw in pipeline_spec(args.workload)]
+    data = synth_volumes(b, size, pin=False)
+    batch = tio.SubjectsBatch({"t1": tio.ImagesBatch(data, [tio.AffineMatrix() for _ in range(b)])})
+    resident = data.to(dev)
+
+    def one_step():
+        history = []
+        for t in transforms:
+            torch.rand(1)
+            history.append({"name": type(t).__name__, "params": t.make_params(batch)})
+        images = {"t1": {"kind": "scalar", "data": resident, "affines": [np.eye(4) for _ in range(b)]}}
+        with warnings.catch_warnings(), torch.device(dev):
+            warnings.simplefilter("ignore")
+            torch_port.replay(images, history)
+        return images["t1"]["data"]
+
+    torch.manual_seed(99)
+    one_step()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        one_step()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    torch.cuda.empty_cache()
+    return {
+        "value": b * size**3 / times[1],
+        "unit": "voxels/s",
+        "kind": "port-on-cuda",
+        "sample": f"median of 3 steps of batch {b} x 1x{size}^3 fp32, same Compose, torch {torch.__version__}"
+                  " CUDA ops (ATen sm_100 kernels) on the same GPU, inputs resident, host randn + H2D as the reference does",
+        "seconds_per_step": times[1],
+        "spread_s": [times[0], times[-1]],
+    }
 
 
 # ----------------------------------------------------------------------------
@@ -353,9 +592,9 @@ def cpu_reference(args, steps, warmup):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: ~13 s per step at batch 2 on the GPU box's 128 host threads; keep the
-    # whole --steps run within a few minutes by dropping to one volume for long runs
-    b = args.cpu_sample_batch if steps * args.cpu_sample_batch <= 24 else 1
+    # bounded sample: ~13 s per step at batch 2 on the GPU box's 128 host threads; one volume per
+    # step for long runs keeps the whole --steps run within a few minutes
+    b = args.cpu_sample_batch if steps * args.cpu_sample_batch <= 12 else 1
     size = args.size
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -378,20 +617,28 @@ def cpu_reference(args, steps, warmup):
             torch_port.replay(images, history)
 
     torch.manual_seed(99)
-    for _ in range(warmup):
+    for _ in range(max(warmup, 1)):
         one_step()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         one_step()
-    dt = time.perf_counter() - t0
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    ordered = sorted(times)
+    median = ordered[len(ordered) // 2]
     return {
-        "value": b * size**3 * steps / dt,
+        "value": b * size**3 / median,
         "unit": "voxels/s",
         "cores": cores,
         "kind": "port",
-        "sample": f"{steps} step(s) of batch {b} x 1x{size}^3 fp32, same Compose, "
-                  f"torch {torch.__version__} CPU ops, {torch.get_num_threads()} threads",
+        "sample": f"median of {steps} step(s) (after {max(warmup, 1)} warm-up) of batch {b} x 1x{size}^3 fp32, "
+                  f"same Compose, torch {torch.__version__} CPU ops, {torch.get_num_threads()} threads",
         "seconds": dt,
+        "batch": b,
+        "median_step_s": median,
+        "spread_step_s": [ordered[0], ordered[-1]],
+        "warmup": max(warmup, 1),
     }
 
 
@@ -406,8 +653,9 @@ def run_reference(args, rank, world):
         "unit": "voxels/s",
         "n_gpus": world,
         "steps": args.steps,
-        "warmup": min(args.warmup, 1),
-        "ms_per_step": base["seconds"] / args.steps * 1e3,
+        "warmup": base["warmup"],
+        "ms_per_step": base["median_step_s"] * 1e3,
+        "step_spread_ms": [x * 1e3 for x in base["spread_step_s"]],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -415,7 +663,7 @@ def run_reference(args, rank, world):
         "data": "synthetic",
         "config": {
             "workload": "bounded sample of the same Compose: batch %d of 1x%d^3 per step on the"
-                        " host cores (rank 0 only)" % (args.cpu_sample_batch, args.size),
+                        " host cores (rank 0 only); value = voxels per MEDIAN step" % (base["batch"], args.size),
             "parallelism": "host threads",
         },
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},

@@ -231,12 +231,12 @@ def coarse_bias_fields(shape, std, seed, scale):
             g = torch.Generator(device="cpu")
             g.manual_seed(sd)
             fields.append(
-                torch.normal(mean=0.0, std=s, size=(1, c, *small), generator=g)
+                torch.normal(mean=0.0, std=s, size=(1, c, *small), generator=g, device="cpu")
             )
         return torch.cat(fields, 0)
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
-    return torch.normal(mean=0.0, std=std, size=(b, c, *small), generator=g)
+    return torch.normal(mean=0.0, std=std, size=(b, c, *small), generator=g, device="cpu")
 
 
 def bias_field(images: dict, params: dict, divide: bool = False) -> None:
@@ -253,7 +253,7 @@ def bias_field(images: dict, params: dict, divide: bool = False) -> None:
             identity = [s == 0 for s in std]
             if all(identity):
                 continue
-            coarse = coarse_bias_fields(data.shape, std, seed, scale)
+            coarse = coarse_bias_fields(data.shape, std, seed, scale).to(data.device)
             field = torch.exp(
                 F.interpolate(
                     coarse, size=list(data.shape[2:]), mode="trilinear",
@@ -265,7 +265,7 @@ def bias_field(images: dict, params: dict, divide: bool = False) -> None:
                 mask = torch.tensor(identity, dtype=torch.bool)
                 out[mask] = data[mask]
         else:
-            coarse = coarse_bias_fields(data.shape, std, seed, scale)
+            coarse = coarse_bias_fields(data.shape, std, seed, scale).to(data.device)
             field = torch.exp(
                 F.interpolate(
                     coarse, size=list(data.shape[2:]), mode="trilinear",
@@ -388,9 +388,10 @@ def noise(images: dict, params: dict) -> None:
         if img["kind"] != "scalar":
             continue
         x = img["data"]
-        n1 = mean + std * torch.randn(x.shape, generator=g)
+        # the reference draws on the CPU generator whatever the data's device (noise.py:166-178)
+        n1 = mean + std * torch.randn(x.shape, generator=g, device="cpu").to(x.device)
         if params.get("rician", False):
-            n2 = mean + std * torch.randn(x.shape, generator=g)
+            n2 = mean + std * torch.randn(x.shape, generator=g, device="cpu").to(x.device)
             y = torch.sqrt((x + n1) ** 2 + n2**2)
         else:
             y = x + n1

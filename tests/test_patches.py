@@ -199,3 +199,73 @@ def test_weighted_label_grid_samplers_match_reference_on_device():
     for i, (index, total) in enumerate(gold["grid_padded"]):
         assert list(gp.locations[i].index) == index
         assert float(gp[i].t1.data.double().sum()) == pytest.approx(total, rel=1e-12)
+
+
+def test_queue_honours_the_samplers_own_limit_and_overridden_call():
+    """`islice(sampler(subject), patches_per_volume)` semantics (data/queue.py:140-146): the
+    sampler's ``num_patches`` caps the count, and a subclass's ``__call__`` is what runs."""
+    import torchio_b200 as tio
+
+    case = PATCH_CASES[1]
+    subjects = _subjects(case)
+    capped = tio.UniformSampler(subjects[0], patch_size=case["patch_size"], num_patches=2)
+    q = tio.Queue(subjects, capped, max_length=50, patches_per_volume=5, shuffle_subjects=False,
+                  shuffle_patches=False)
+    torch.manual_seed(0)
+    assert len(list(q)) == 2 * len(subjects)
+
+    class FirstCorner(tio.UniformSampler):
+        def __call__(self, subject, num_patches=None):
+            while True:
+                yield self._extract_patch(subject, tio.PatchLocation(index=(0, 0, 0), size=self.patch_size))
+
+    q = tio.Queue(subjects, FirstCorner(subjects[0], patch_size=case["patch_size"]), max_length=50,
+                  patches_per_volume=3, shuffle_subjects=False, shuffle_patches=False)
+    got = list(q)
+    assert len(got) == 3 * len(subjects) and all(p.patch_location.index == (0, 0, 0) for p in got)
+    # a patch larger than the volume is the reference's clamped view, not an error
+    big = tio.UniformSampler(subjects[0], patch_size=(64, 8, 8))
+    torch.manual_seed(0)
+    patch = next(iter(tio.Queue(subjects, big, patches_per_volume=1, shuffle_subjects=False)))
+    assert tuple(patch.t1.data.shape[1:]) == (case["shape"][0], 8, 8)
+
+
+@pytest.mark.gpu
+def test_device_queue_uses_the_patch_ring_and_collates_with_one_gather():
+    """Device subjects: patches live in ring slots (no per-patch tensors), the loader's batches come
+    from one index_select per image, slots are reused after a flush, handles behave like Subjects."""
+    import torchio_b200 as tio
+    from torchio_b200.patches import PatchHandle
+
+    case = PATCH_CASES[0]
+    subjects = _subjects(case, "cuda")
+    queue = _queue(case, subjects)
+    torch.manual_seed(case["seed"])
+    random.seed(case["seed"])
+    handles = list(queue)
+    assert all(isinstance(h, PatchHandle) for h in handles)
+    ring = handles[0].ring
+    assert ring.capacity == case["max_length"] + case["patches_per_volume"] - 1
+    assert all(h.ring is ring for h in handles) and max(h.slot for h in handles) < ring.capacity
+    # the last flush is still in the ring: handle views equal a fresh crop of the volume
+    last = handles[-1]
+    sid, (i, j, k) = int(last.sid), last.patch_location.index
+    pi, pj, pk = case["patch_size"]
+    assert torch.equal(last.t1.data, subjects[sid].t1.data[:, i:i + pi, j:j + pj, k:k + pk])
+    assert last.t1.data.data_ptr() == ring.data["t1"][last.slot].data_ptr()  # a view, not a copy
+    # collate: same batches as stacking materialised patches
+    torch.manual_seed(case["seed"])
+    random.seed(case["seed"])
+    loader = tio.SubjectsLoader(queue, batch_size=case["batch_size"])
+    torch.manual_seed(case["seed"])
+    random.seed(case["seed"])
+    reference = tio.SubjectsLoader(_queue(case, _subjects(case, "cpu")), batch_size=case["batch_size"])
+    n = 0
+    for got, want in zip(loader, reference):
+        assert torch.equal(got.t1.data.cpu(), want.t1.data) and torch.equal(got.seg.data.cpu(), want.seg.data)
+        assert [l.index for l in got.metadata["patch_location"]] == [l.index for l in want.metadata["patch_location"]]
+        assert got.metadata["sid"] == want.metadata["sid"]
+        for a, b in zip(got.t1.affines, want.t1.affines):
+            assert np.allclose(a.numpy(), b.numpy(), rtol=0, atol=1e-12)
+        n += got.batch_size
+    assert n == queue.patches_per_epoch

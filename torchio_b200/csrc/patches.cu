@@ -10,11 +10,11 @@
 
 namespace tio {
 
+// General path: one thread row-group per (patch, channel, i, j) row, threads along k.
 template <typename T>
 __global__ void __launch_bounds__(256)
 crop_patches_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int I, int J, int K, int n,
                     const int32_t* __restrict__ corners, int pi, int pj, int pk) {
-  // one CTA row-group: blockIdx.x -> (patch, channel, i, group of rows j), threads run along k
   const int rows_per_block = blockDim.y;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.y;  // over n*C*pi*pj
   const long long total_rows = (long long)n * C * pi * pj;
@@ -29,10 +29,49 @@ crop_patches_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int I
   for (int k = threadIdx.x; k < pk; k += blockDim.x) d[k] = s[k];
 }
 
+// 16 bytes per thread (rows that are multiples of 16 bytes, 16-byte aligned destination): one
+// 128-bit store per thread; the source row starts wherever the corner puts it, so it is read
+// with one 128-bit load when that address happens to be aligned and element by element
+// otherwise (a warp still reads one contiguous 512-byte span either way).
+template <typename T>
+__global__ void __launch_bounds__(256)
+crop_patches_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int I, int J, int K,
+                        long long units, const int32_t* __restrict__ corners, int pi, int pj, int pk) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over n*C*pi*pj*(pk/V)
+  if (u >= units) return;
+  const int per_row = pk / V;
+  const long long row = u / per_row;
+  const int kq = (int)(u - row * per_row) * V;
+  const int j = (int)(row % pj);
+  const int i = (int)((row / pj) % pi);
+  const int c = (int)((row / ((long long)pj * pi)) % C);
+  const int p = (int)(row / ((long long)pj * pi * C));
+  const int ci = __ldg(corners + 3 * p), cj = __ldg(corners + 3 * p + 1), ck = __ldg(corners + 3 * p + 2);
+  const T* s = src + (((long long)c * I + (ci + i)) * J + (cj + j)) * K + ck + kq;
+  uint4 v;
+  if (((uintptr_t)s & 15) == 0) {
+    v = __ldg(reinterpret_cast<const uint4*>(s));
+  } else {
+    T t[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) t[e] = __ldg(s + e);
+    memcpy(&v, t, 16);
+  }
+  *reinterpret_cast<uint4*>(dst + row * pk + kq) = v;
+}
+
 template <typename T>
 static void launch_crop(const void* src, void* dst, int C, int I, int J, int K, int n,
                         const int32_t* corners, int pi, int pj, int pk, cudaStream_t st) {
   const long long rows = (long long)n * C * pi * pj;
+  constexpr int V = 16 / (int)sizeof(T);
+  if (pk % V == 0 && ((uintptr_t)dst & 15) == 0) {
+    const long long units = rows * (pk / V);
+    const unsigned blocks = (unsigned)((units + 255) / 256);
+    crop_patches_vec_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (T*)dst, C, I, J, K, units, corners, pi, pj, pk);
+    return;
+  }
   const int tx = pk >= 128 ? 128 : (pk >= 64 ? 64 : 32);
   dim3 block(tx, 256 / tx);
   const unsigned blocks = (unsigned)((rows + block.y - 1) / block.y);
@@ -51,6 +90,7 @@ extern "C" int tio_crop_patches(const void* src, void* dst, int elem_bytes, int 
   TIO_CHECK_ARG(pi > 0 && pj > 0 && pk > 0 && pi <= I && pj <= J && pk <= K,
                 "tio_crop_patches: patch (%d,%d,%d) does not fit the volume (%d,%d,%d)", pi, pj, pk, I, J, K);
   TIO_CHECK_ARG((long long)n * C * pi * pj / 2 < (1ll << 31), "tio_crop_patches: too many rows");
+  TIO_CHECK_ARG((long long)n * C * pi * pj * ((pk + 3) / 4) / 256 < (1ll << 31), "tio_crop_patches: too many elements");
   cudaStream_t st = (cudaStream_t)stream;
   switch (elem_bytes) {
     case 1: launch_crop<uint8_t>(src, dst, C, I, J, K, n, corners, pi, pj, pk, st); break;

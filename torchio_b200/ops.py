@@ -227,10 +227,11 @@ def min_sample0(src: Tensor) -> Tensor:
     return fill
 
 
-def crop_patches(volume: Tensor, corners, size) -> Tensor:
+def crop_patches(volume: Tensor, corners, size, out: Tensor | None = None) -> Tensor:
     """Gather ``n`` patches of ``size`` at voxel ``corners`` (n,3) from one volume
     (C,I,J,K) into a dense (n,C,*size) block in a single launch
-    (data/sampler.py:54-67 + loader.py:15-24)."""
+    (data/sampler.py:54-67 + loader.py:15-24).  ``out``: a contiguous (n,C,*size) block to
+    write into (e.g. consecutive slots of a patch ring) instead of a fresh tensor."""
     _require_cuda(volume, "crop_patches")
     if volume.ndim != 4:
         raise ValueError(f"crop_patches expects a (C, I, J, K) volume, got {tuple(volume.shape)}")
@@ -244,7 +245,13 @@ def crop_patches(volume: Tensor, corners, size) -> Tensor:
     if corners.min() < 0 or np.any(corners + np.asarray([pi, pj, pk]) > np.asarray([i, j, k])):
         raise ValueError("crop_patches: a patch extends beyond the volume")
     (corners_d,) = upload(volume.device, corners)
-    dst = torch.empty((n, c, pi, pj, pk), dtype=volume.dtype, device=volume.device)
+    if out is None:
+        dst = torch.empty((n, c, pi, pj, pk), dtype=volume.dtype, device=volume.device)
+    else:
+        dst = out
+        if (tuple(dst.shape) != (n, c, pi, pj, pk) or dst.dtype != volume.dtype or dst.device != volume.device
+                or not dst.is_contiguous()):
+            raise ValueError("crop_patches: `out` must be a contiguous (n, C, *size) block of the volume's dtype/device")
     with torch.cuda.device(volume.device):
         _native.call(
             "tio_crop_patches", _ptr(volume), _ptr(dst), volume.element_size(), c, i, j, k, n,

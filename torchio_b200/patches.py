@@ -6,14 +6,14 @@ reference (patch corners come from the global torch CPU generator, three
 ``torch.randint`` calls per patch in i, j, k order — data/sampler.py:218-223;
 subject and buffer shuffles use Python's ``random`` — data/queue.py:167,177).
 
-Difference by design: when a subject's tensors live on the GPU, the patches a
-`Queue` asks for (``patches_per_volume`` at a time) are gathered by one
-`ops.crop_patches` launch per image into a dense block and handed out as views
-of that block, instead of one strided view per patch that ``torch.stack``
-copies again at collation.  Host-resident subjects keep the reference's
-zero-copy views.  ``Queue(device=...)`` (extension) moves each loaded subject to
-that device before the transform, so augmentation and patch extraction run
-resident.
+Difference by design: when a subject's tensors live on the GPU, a `Queue` holds
+its patches in a pre-allocated device ring (`PatchRing`): one `ops.crop_patches`
+launch per image writes the ``patches_per_volume`` patches of a subject straight into
+consecutive slots, the buffer shuffle permutes slot indices, and `collate_subjects`
+builds a batch with one ``index_select`` per image — no per-patch `Subject`, no
+``torch.stack``.  Host-resident subjects keep the reference's zero-copy views.
+``Queue(device=...)`` (extension) moves each loaded subject to that device before
+the transform, so augmentation and patch extraction run resident.
 """
 
 from __future__ import annotations
@@ -31,7 +31,7 @@ import torch
 from torch.utils.data import DataLoader, Dataset, IterableDataset, Sampler
 
 from . import ops
-from .data import ImagesBatch, Subject, SubjectsBatch
+from .data import AffineMatrix, ImagesBatch, Subject, SubjectsBatch
 
 
 @dataclass(frozen=True)
@@ -89,7 +89,8 @@ class PatchSampler:
         images = subject.images
         on_device = all(img.data.is_cuda for img in images.values())
         same_size = all(loc.size == locations[0].size for loc in locations)
-        if not (on_device and same_size):
+        fits = all(p <= s for p, s in zip(locations[0].size, subject.spatial_shape))
+        if not (on_device and same_size and fits):  # (an oversized patch is a clamped view, as upstream)
             return [self._extract_patch(subject, loc) for loc in locations]
         corners = np.asarray([loc.index for loc in locations], dtype=np.int32)
         blocks = {name: ops.crop_patches(img.data, corners, locations[0].size) for name, img in images.items()}
@@ -125,13 +126,16 @@ class UniformSampler(PatchSampler, IterableDataset):
     def __iter__(self) -> Iterator[Subject]:
         return self(self.subject, self.num_patches)
 
+    def draw_locations(self, subject: Subject, count: int) -> list[PatchLocation]:
+        """The locations of the first ``count`` patches ``self(subject)`` would yield (same draws)."""
+        shape = subject.spatial_shape
+        return [PatchLocation(index=self._random_index(shape), size=self.patch_size) for _ in range(count)]
+
     def sample(self, subject: Subject, num_patches: int) -> list[Subject]:
         """``list(islice(self(subject), num_patches))`` with the same RNG draws, the
         patches of a device-resident subject gathered in one launch per image."""
-        shape = subject.spatial_shape
-        locations = [PatchLocation(index=self._random_index(shape), size=self.patch_size)
-                     for _ in range(num_patches)]
-        return self._extract_patches(subject, locations)
+        count = num_patches if not self.num_patches else min(num_patches, self.num_patches)
+        return self._extract_patches(subject, self.draw_locations(subject, count))
 
     def _random_index(self, spatial_shape) -> tuple[int, int, int]:
         def _rand(d: int) -> int:
@@ -246,11 +250,16 @@ class WeightedSampler(PatchSampler, IterableDataset):
     def __iter__(self) -> Iterator[Subject]:
         return self(self.subject, self.num_patches)
 
+    def draw_locations(self, subject: Subject, count: int) -> list[PatchLocation]:
+        """The locations of the first ``count`` patches ``self(subject)`` would yield (same draws)."""
+        flat, shape = self._flat_map(subject)
+        return [self._draw(flat, shape, subject) for _ in range(count)]
+
     def sample(self, subject: Subject, num_patches: int) -> list[Subject]:
         """``list(islice(self(subject), num_patches))``, same draws, one gather launch per
         image for a device-resident subject."""
-        flat, shape = self._flat_map(subject)
-        return self._extract_patches(subject, [self._draw(flat, shape, subject) for _ in range(num_patches)])
+        count = num_patches if not self.num_patches else min(num_patches, self.num_patches)
+        return self._extract_patches(subject, self.draw_locations(subject, count))
 
     def _build_probability_map_for(self, subject: Subject) -> torch.Tensor:
         prob_data = subject.images[self.probability_map].data[0].float()
@@ -280,8 +289,157 @@ class LabelSampler(WeightedSampler):
         return _mask_borders(prob, subject.spatial_shape, self.patch_size)
 
 
+# samplers whose ``__call__`` the ring path may bypass (a subclass that overrides it is iterated)
+_STOCK_CALLS = {"UniformSampler": UniformSampler.__call__, "WeightedSampler": WeightedSampler.__call__,
+                "LabelSampler": WeightedSampler.__call__}
+
+
+# ---------------------------------------------------------------------------------------
+# Queue: patch buffer for stochastic patch-based training (data/queue.py:21-208)
+#
+# What the reference does per epoch: subjects (optionally shuffled with `random.shuffle`, or in
+# the order of `subject_sampler`) are loaded and transformed one by one, `patches_per_volume`
+# patches of each are appended to a buffer, and whenever the buffer holds `max_length` patches
+# or more it is shuffled (`random.shuffle`) and handed out from the back until it is empty.
+# That order is the contract (tests/golden/patches_*.npz).  How the patches are held is not:
+#
+#   * host-resident subjects: the buffer holds the sampler's zero-copy views, as upstream;
+#   * device-resident subjects (or `device=`): the buffer is a pre-allocated RING of patch
+#     slots per image, `(max_length + patches_per_volume - 1, C, *patch_size)` on the device.
+#     One `tio_crop_patches` launch per image writes a subject's patches straight into
+#     consecutive slots; the shuffle permutes slot indices (same `random.shuffle` call on a
+#     list of the same length, hence the same order); the queue hands out `PatchHandle`s
+#     (slot + location + a reference to the per-subject record) and `collate_subjects` turns a
+#     list of handles into a `SubjectsBatch` with ONE `index_select` per image.  No per-patch
+#     `Subject`, no per-patch tensor, no `torch.stack`.
+# ---------------------------------------------------------------------------------------
+
+
+class _SubjectRecord:
+    """What the patches of one subject share: image classes / affines / metadata / history."""
+
+    __slots__ = ("kinds", "affines", "image_metadata", "metadata", "history")
+
+    def __init__(self, subject: Subject) -> None:
+        self.kinds = {name: type(img) for name, img in subject.images.items()}
+        self.affines = {name: img.affine.numpy() for name, img in subject.images.items()}
+        self.image_metadata = {name: dict(img.metadata) for name, img in subject.images.items()}
+        self.metadata = dict(subject.metadata)
+        self.history = list(subject.applied_transforms)
+
+    def patch_affine(self, name: str, index) -> np.ndarray:
+        matrix = self.affines[name].copy()
+        matrix[:3, 3] = matrix[:3, 3] + matrix[:3, :3] @ np.asarray(index, dtype=np.float64)
+        return matrix
+
+
+class PatchRing:
+    """Device-side patch slots of one Queue: ``data[name]`` is ``(capacity, C, *patch_size)``."""
+
+    def __init__(self, capacity: int, patch_size, subject: Subject) -> None:
+        self.capacity = int(capacity)
+        self.patch_size = tuple(patch_size)
+        self.data = {
+            name: torch.empty((self.capacity, img.data.shape[0], *self.patch_size), dtype=img.data.dtype,
+                              device=img.data.device)
+            for name, img in subject.images.items()
+        }
+        self.filled = 0
+
+    def matches(self, subject: Subject) -> bool:
+        return (set(subject.images) == set(self.data) and all(
+            self.data[n].dtype == img.data.dtype and self.data[n].device == img.data.device
+            and self.data[n].shape[1] == img.data.shape[0] for n, img in subject.images.items()))
+
+    def write(self, subject: Subject, locations: list[PatchLocation]) -> range:
+        """One gather launch per image into the next ``len(locations)`` slots."""
+        n = len(locations)
+        if self.filled + n > self.capacity:
+            raise RuntimeError("PatchRing overflow (queue invariant broken)")
+        corners = np.asarray([loc.index for loc in locations], dtype=np.int32)
+        slots = range(self.filled, self.filled + n)
+        for name, img in subject.images.items():
+            ops.crop_patches(img.data, corners, self.patch_size, out=self.data[name][slots.start:slots.stop])
+        self.filled += n
+        return slots
+
+
+class PatchHandle:
+    """A patch that lives in a `PatchRing` slot.  `collate_subjects` batches handles without
+    materialising them; any `Subject` attribute (``handle.t1``, ``handle.patch_location``,
+    ``handle.sid`` ...) materialises a `Subject` of VIEWS of the slot on first use.  The slot is
+    rewritten once the queue has handed out the rest of its buffer and refills: keep
+    ``handle.subject(copy=True)`` if the data must outlive that."""
+
+    __slots__ = ("ring", "slot", "location", "record", "_subject")
+
+    def __init__(self, ring: PatchRing, slot: int, location: PatchLocation, record: _SubjectRecord) -> None:
+        self.ring, self.slot, self.location, self.record = ring, slot, location, record
+        self._subject = None
+
+    def subject(self, copy: bool = False) -> Subject:
+        if self._subject is None or copy:
+            rec = self.record
+            kwargs: dict[str, Any] = {}
+            for name, block in self.ring.data.items():
+                data = block[self.slot].clone() if copy else block[self.slot]
+                kwargs[name] = rec.kinds[name](data, affine=rec.patch_affine(name, self.location.index),
+                                               **rec.image_metadata[name])
+            kwargs.update(rec.metadata)
+            kwargs["patch_location"] = self.location
+            built = Subject(**kwargs)
+            built.applied_transforms = list(rec.history)
+            if copy:
+                return built
+            self._subject = built
+        return self._subject
+
+    def __getattr__(self, name: str):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.subject(), name)
+
+
+class _ViewBuffer:
+    """Reference behaviour: the buffer is a list of patch Subjects (views of their volume)."""
+
+    def __init__(self) -> None:
+        self.items: list[Any] = []
+
+    def __len__(self) -> int:
+        return len(self.items)
+
+    def add(self, patches: list[Any]) -> None:
+        self.items.extend(patches)
+
+    def drain(self, shuffle: bool) -> Iterator[Any]:
+        if shuffle:
+            _random.shuffle(self.items)
+        while self.items:
+            yield self.items.pop()
+
+
+class _RingBuffer(_ViewBuffer):
+    """Same order of hand-out, patches held as ring slots."""
+
+    def __init__(self, ring: PatchRing) -> None:
+        super().__init__()
+        self.ring = ring
+
+    def add_subject(self, subject: Subject, locations: list[PatchLocation]) -> None:
+        record = _SubjectRecord(subject)
+        slots = self.ring.write(subject, locations)
+        self.items.extend(PatchHandle(self.ring, slot, loc, record) for slot, loc in zip(slots, locations))
+
+    def drain(self, shuffle: bool) -> Iterator[Any]:
+        yield from super().drain(shuffle)
+        self.ring.filled = 0  # every slot has been handed out: refill from the start
+
+
 class Queue(IterableDataset):
-    """Patch buffer for stochastic patch-based training (data/queue.py:21-208)."""
+    """Same constructor, same order of patches as the reference's Queue; ``device=`` (extension)
+    moves a copy of each loaded subject to that device before the transform, so augmentation and
+    patch extraction run resident and the buffer is a device patch ring (see above)."""
 
     def __init__(self, subjects: Sequence[Subject], patch_sampler: PatchSampler, max_length: int = 300,
                  patches_per_volume: int = 10, num_workers: int = 0, shuffle_subjects: bool = True,
@@ -302,47 +460,57 @@ class Queue(IterableDataset):
         self.transform = transform
         self.subject_sampler = subject_sampler
         self.device = None if device is None else torch.device(device)
+        self._ring: PatchRing | None = None
 
-    def __iter__(self) -> Iterator[Subject]:
-        buffer: list[Subject] = []
-        subject_iter = self._make_subject_iter()
-        if self.num_workers > 0:
-            yield from self._iter_threaded(subject_iter, buffer)
-        else:
-            yield from self._iter_sync(subject_iter, buffer)
+    # ---- iteration -------------------------------------------------------------------
 
-    def _iter_sync(self, subject_iter, buffer) -> Iterator[Subject]:
-        for raw in subject_iter:
-            prepared = self._prepare(raw)
-            buffer.extend(self._sample_patches(prepared))
-            yield from self._drain_if_full(buffer)
-        yield from self._flush(buffer)
+    def __iter__(self) -> Iterator[Any]:
+        buffer: _ViewBuffer | None = None
+        for subject in self._prepared():
+            locations = self._ring_locations(subject)
+            if locations is not None:
+                if not isinstance(buffer, _RingBuffer):
+                    if buffer:  # a host-resident stretch came first: hand it out before switching
+                        yield from buffer.drain(self.shuffle_patches)
+                    buffer = _RingBuffer(self._ring_for(subject))
+                buffer.add_subject(subject, locations)
+            else:
+                if isinstance(buffer, _RingBuffer) or buffer is None:
+                    if buffer:
+                        yield from buffer.drain(self.shuffle_patches)
+                    buffer = _ViewBuffer()
+                buffer.add(self._view_patches(subject))
+            if len(buffer) >= self.max_length:
+                yield from buffer.drain(self.shuffle_patches)
+        if buffer:
+            yield from buffer.drain(self.shuffle_patches)
 
-    def _iter_threaded(self, subject_iter, buffer) -> Iterator[Subject]:
+    def _prepared(self) -> Iterator[Subject]:
+        """Loaded (+ moved, + transformed) subjects in epoch order.  ``num_workers`` threads
+        prepare ahead; results are consumed strictly in order, so the patch order does not depend
+        on thread timing (the reference's threaded mode flushes at timing-dependent points)."""
+        order = self._epoch_order()
+        if self.num_workers <= 0:
+            for subject in order:
+                yield self._prepare(subject)
+            return
+        window = 2 * self.num_workers
         with ThreadPoolExecutor(max_workers=self.num_workers) as pool:
-            futures: deque[Future[Subject]] = deque()
-            for raw in subject_iter:
-                futures.append(pool.submit(self._prepare, raw))
-                yield from self._collect_ready(futures, buffer)
-                yield from self._drain_if_full(buffer)
-            for future in futures:
-                buffer.extend(self._sample_patches(future.result()))
-        yield from self._flush(buffer)
+            pending: deque[Future[Subject]] = deque()
+            for subject in order:
+                pending.append(pool.submit(self._prepare, subject))
+                if len(pending) >= window:
+                    yield pending.popleft().result()
+            while pending:
+                yield pending.popleft().result()
 
-    def _collect_ready(self, futures, buffer) -> Iterator[Subject]:
-        while futures and futures[0].done():
-            buffer.extend(self._sample_patches(futures.popleft().result()))
-        return iter(())
-
-    def _drain_if_full(self, buffer) -> Iterator[Subject]:
-        if len(buffer) >= self.max_length:
-            yield from self._flush(buffer)
-
-    def _flush(self, buffer) -> Iterator[Subject]:
-        if self.shuffle_patches:
-            _random.shuffle(buffer)
-        while buffer:
-            yield buffer.pop()
+    def _epoch_order(self) -> Iterator[Subject]:
+        if self.subject_sampler is not None:
+            return (self.subjects[i] for i in list(self.subject_sampler))
+        subjects = list(self.subjects)
+        if self.shuffle_subjects:
+            _random.shuffle(subjects)
+        return iter(subjects)
 
     def _prepare(self, subject: Subject) -> Subject:
         subject.load()
@@ -358,19 +526,41 @@ class Queue(IterableDataset):
             subject = self.transform(subject)
         return subject
 
-    def _sample_patches(self, subject: Subject) -> list[Subject]:
-        batched = getattr(self.patch_sampler, "sample", None)
-        if batched is not None:
-            return batched(subject, self.patches_per_volume)
+    # ---- patches of one subject ------------------------------------------------------
+
+    def _count(self) -> int:
+        """``islice(sampler(subject), patches_per_volume)`` stops at the sampler's own
+        ``num_patches`` when that is smaller."""
+        own = getattr(self.patch_sampler, "num_patches", None)
+        return self.patches_per_volume if not own else min(self.patches_per_volume, int(own))
+
+    def _ring_locations(self, subject: Subject) -> list[PatchLocation] | None:
+        """Patch locations drawn exactly as iterating the sampler would, when the ring applies:
+        device-resident subject, a stock sampler (its ``__call__`` not overridden), patches that
+        fit the volume.  None = take the sampler's own patches (views)."""
+        sampler = self.patch_sampler
+        draw = getattr(sampler, "draw_locations", None)
+        stock = _STOCK_CALLS.get(type(sampler).__mro__[0].__name__)
+        if draw is None or stock is None or type(sampler).__call__ is not stock:
+            return None
+        if not all(img.data.is_cuda for img in subject.images.values()):
+            return None
+        if any(p > s for p, s in zip(sampler.patch_size, subject.spatial_shape)):
+            return None
+        return draw(subject, self._count())
+
+    def _view_patches(self, subject: Subject) -> list[Subject]:
         return list(islice(iter(self.patch_sampler(subject)), self.patches_per_volume))
 
-    def _make_subject_iter(self) -> Iterator[Subject]:
-        if self.subject_sampler is not None:
-            return (self.subjects[i] for i in list(self.subject_sampler))
-        subjects = list(self.subjects)
-        if self.shuffle_subjects:
-            _random.shuffle(subjects)
-        return iter(subjects)
+    def _ring_for(self, subject: Subject) -> PatchRing:
+        ring = self._ring
+        if ring is None or not ring.matches(subject) or ring.patch_size != tuple(self.patch_sampler.patch_size):
+            capacity = self.max_length + self.patches_per_volume - 1
+            ring = self._ring = PatchRing(capacity, self.patch_sampler.patch_size, subject)
+        ring.filled = 0
+        return ring
+
+    # ---- bookkeeping the reference exposes -------------------------------------------
 
     @property
     def num_subjects(self) -> int:
@@ -387,26 +577,37 @@ class Queue(IterableDataset):
 
     @property
     def max_memory(self) -> int:
-        sample = self.subjects[0]
-        channels = sum(img.num_channels for img in sample.images.values())
-        voxels = 1
-        for s in self.patch_sampler.patch_size:
-            voxels *= s
-        return 4 * channels * voxels * self.max_length
+        """Bytes of ``max_length`` fp32 patches of the first subject's channels (queue.py:195-203)."""
+        channels = sum(img.num_channels for img in self.subjects[0].images.values())
+        return 4 * channels * int(np.prod(self.patch_sampler.patch_size)) * self.max_length
 
     @property
     def max_memory_pretty(self) -> str:
-        value = float(self.max_memory)
-        for unit in ("Bytes", "KiB", "MiB", "GiB", "TiB"):
-            if value < 1024 or unit == "TiB":
-                return f"{value:.0f} {unit}" if unit == "Bytes" else f"{value:.1f} {unit}"
-            value /= 1024
-        return f"{value:.1f} TiB"
+        value, units = float(self.max_memory), ("Bytes", "KiB", "MiB", "GiB", "TiB")
+        step = 0
+        while value >= 1024 and step < len(units) - 1:
+            value, step = value / 1024, step + 1
+        return f"{value:.0f} Bytes" if step == 0 else f"{value:.1f} {units[step]}"
 
 
 def collate_subjects(batch: Sequence[Any]) -> SubjectsBatch:
-    """List of Subjects -> SubjectsBatch with stacked 5-D tensors (loader.py:15-24)."""
-    return SubjectsBatch.from_subjects(list(batch))
+    """List of patches/subjects -> SubjectsBatch (loader.py:15-24).  Handles of one patch ring are
+    batched with one ``index_select`` per image; anything else goes through ``from_subjects``."""
+    items = list(batch)
+    if items and all(isinstance(item, PatchHandle) for item in items) and all(
+            item.ring is items[0].ring for item in items):
+        ring = items[0].ring
+        slots = torch.tensor([item.slot for item in items], dtype=torch.int64)
+        images = {}
+        for name, block in ring.data.items():
+            data = block.index_select(0, slots.to(block.device, non_blocking=True))
+            affines = [AffineMatrix(item.record.patch_affine(name, item.location.index)) for item in items]
+            images[name] = ImagesBatch(data, affines, image_class=items[0].record.kinds[name])
+        keys = list(items[0].record.metadata)
+        metadata = {k: [item.record.metadata[k] for item in items] for k in keys}
+        metadata["patch_location"] = [item.location for item in items]
+        return SubjectsBatch(images, metadata=metadata)
+    return SubjectsBatch.from_subjects([item.subject() if isinstance(item, PatchHandle) else item for item in items])
 
 
 def collate_images(batch: Sequence[Any]) -> ImagesBatch:
