@@ -484,7 +484,7 @@ def queue_unet_leg(args, dev, tio):
     for i in range(n_subjects):
         g = torch.Generator().manual_seed(2000 + i)
         subjects.append(tio.Subject(t1=tio.ScalarImage(torch.rand((1, size, size, size), generator=g))))
-    sampler = tio.UniformSampler(patch)
+    sampler = tio.UniformSampler(subjects[0], patch)
     queue = tio.Queue(subjects, max_length=max_length, patches_per_volume=per_volume, patch_sampler=sampler,
                       transform=pipe, num_workers=0, shuffle_subjects=False, shuffle_patches=True, device=dev)
     loader = tio.SubjectsLoader(queue, batch_size=batch_size)

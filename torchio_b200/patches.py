@@ -19,6 +19,7 @@ the transform, so augmentation and patch extraction run resident.
 from __future__ import annotations
 
 import random as _random
+import weakref
 from collections import deque
 from collections.abc import Iterator, Sequence, Sized
 from concurrent.futures import Future, ThreadPoolExecutor
@@ -345,6 +346,15 @@ class PatchRing:
             for name, img in subject.images.items()
         }
         self.filled = 0
+        self._handed_out: weakref.WeakSet = weakref.WeakSet()  # handles whose slot is still theirs
+
+    def recycle(self) -> None:
+        """Start refilling from slot 0.  Handles of the previous fill that the caller still holds
+        (e.g. ``list(queue)``) take a private copy of their slot first, so they stay valid."""
+        for handle in list(self._handed_out):
+            handle.detach()
+        self._handed_out = weakref.WeakSet()
+        self.filled = 0
 
     def matches(self, subject: Subject) -> bool:
         return (set(subject.images) == set(self.data) and all(
@@ -367,17 +377,26 @@ class PatchRing:
 class PatchHandle:
     """A patch that lives in a `PatchRing` slot.  `collate_subjects` batches handles without
     materialising them; any `Subject` attribute (``handle.t1``, ``handle.patch_location``,
-    ``handle.sid`` ...) materialises a `Subject` of VIEWS of the slot on first use.  The slot is
-    rewritten once the queue has handed out the rest of its buffer and refills: keep
-    ``handle.subject(copy=True)`` if the data must outlive that."""
+    ``handle.sid`` ...) materialises a `Subject` of VIEWS of the slot on first use.  When the
+    queue refills the ring, handles that are still referenced copy their slot out first
+    (`detach`), so a patch stays valid for as long as it is held, like the reference's views."""
 
-    __slots__ = ("ring", "slot", "location", "record", "_subject")
+    __slots__ = ("ring", "slot", "location", "record", "_subject", "__weakref__")
 
     def __init__(self, ring: PatchRing, slot: int, location: PatchLocation, record: _SubjectRecord) -> None:
         self.ring, self.slot, self.location, self.record = ring, slot, location, record
         self._subject = None
+        ring._handed_out.add(self)
+
+    def detach(self) -> None:
+        """Own the data: a private copy of the slot replaces the views."""
+        if self.ring is not None:
+            self._subject = self.subject(copy=True)
+            self.ring = None
 
     def subject(self, copy: bool = False) -> Subject:
+        if self.ring is None:
+            return self._subject
         if self._subject is None or copy:
             rec = self.record
             kwargs: dict[str, Any] = {}
@@ -427,13 +446,14 @@ class _RingBuffer(_ViewBuffer):
         self.ring = ring
 
     def add_subject(self, subject: Subject, locations: list[PatchLocation]) -> None:
+        self.add_subject_check()
         record = _SubjectRecord(subject)
         slots = self.ring.write(subject, locations)
         self.items.extend(PatchHandle(self.ring, slot, loc, record) for slot, loc in zip(slots, locations))
 
-    def drain(self, shuffle: bool) -> Iterator[Any]:
-        yield from super().drain(shuffle)
-        self.ring.filled = 0  # every slot has been handed out: refill from the start
+    def add_subject_check(self) -> None:
+        if not self.items and self.ring.filled:  # everything was handed out: refill from the start
+            self.ring.recycle()
 
 
 class Queue(IterableDataset):
@@ -557,7 +577,7 @@ class Queue(IterableDataset):
         if ring is None or not ring.matches(subject) or ring.patch_size != tuple(self.patch_sampler.patch_size):
             capacity = self.max_length + self.patches_per_volume - 1
             ring = self._ring = PatchRing(capacity, self.patch_sampler.patch_size, subject)
-        ring.filled = 0
+        ring.recycle()
         return ring
 
     # ---- bookkeeping the reference exposes -------------------------------------------
@@ -594,7 +614,7 @@ def collate_subjects(batch: Sequence[Any]) -> SubjectsBatch:
     """List of patches/subjects -> SubjectsBatch (loader.py:15-24).  Handles of one patch ring are
     batched with one ``index_select`` per image; anything else goes through ``from_subjects``."""
     items = list(batch)
-    if items and all(isinstance(item, PatchHandle) for item in items) and all(
+    if items and all(isinstance(item, PatchHandle) for item in items) and items[0].ring is not None and all(
             item.ring is items[0].ring for item in items):
         ring = items[0].ring
         slots = torch.tensor([item.slot for item in items], dtype=torch.int64)
