@@ -494,6 +494,12 @@ def queue_unet_leg(args, dev, tio):
         nn.ConvTranspose3d(16, 8, 2, stride=2), nn.ReLU(inplace=True), nn.Conv3d(8, 2, 1),
     ).to(dev).to(memory_format=torch.channels_last_3d).half()
     torch.manual_seed(5)
+    with torch.no_grad(), warnings.catch_warnings():  # warm-up: cuDNN plan, kernels, the ring itself
+        warnings.simplefilter("ignore")
+        for batch in tio.SubjectsLoader(tio.Queue(subjects[:2], max_length=max_length, patches_per_volume=per_volume,
+                                                  patch_sampler=sampler, transform=pipe, shuffle_subjects=False,
+                                                  device=dev), batch_size=batch_size):
+            net(batch.images["t1"].data.half().contiguous(memory_format=torch.channels_last_3d))
     n_patches = 0
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -244,14 +244,17 @@ def test_device_queue_uses_the_patch_ring_and_collates_with_one_gather():
     random.seed(case["seed"])
     handles = list(queue)
     assert all(isinstance(h, PatchHandle) for h in handles)
-    ring = handles[0].ring
+    ring = handles[-1].ring
     assert ring.capacity == case["max_length"] + case["patches_per_volume"] - 1
-    assert all(h.ring is ring for h in handles) and max(h.slot for h in handles) < ring.capacity
-    # the last flush is still in the ring: handle views equal a fresh crop of the volume
-    last = handles[-1]
-    sid, (i, j, k) = int(last.sid), last.patch_location.index
+    attached = [h for h in handles if h.ring is ring]
+    detached = [h for h in handles if h.ring is None]  # held across a refill: they own a copy now
+    assert attached and detached and len(attached) + len(detached) == len(handles)
+    assert max(h.slot for h in handles) < ring.capacity
     pi, pj, pk = case["patch_size"]
-    assert torch.equal(last.t1.data, subjects[sid].t1.data[:, i:i + pi, j:j + pj, k:k + pk])
+    for h in (handles[0], handles[-1]):  # a detached one and one still in the ring
+        sid, (i, j, k) = int(h.sid), h.patch_location.index
+        assert torch.equal(h.t1.data, subjects[sid].t1.data[:, i:i + pi, j:j + pj, k:k + pk])
+    last = handles[-1]
     assert last.t1.data.data_ptr() == ring.data["t1"][last.slot].data_ptr()  # a view, not a copy
     # collate: same batches as stacking materialised patches
     torch.manual_seed(case["seed"])

@@ -133,6 +133,14 @@ class AffineMatrix:
     __copy__ = clone
 
 
+def _clone_keeping_pin(t: torch.Tensor) -> torch.Tensor:
+    """``t.clone()``, but a page-locked host tensor stays page-locked: a deep copy of a pinned
+    batch (Transform(copy=True)) must still stream to the device with asynchronous copies."""
+    if t.device.type == "cpu" and t.is_pinned():
+        return torch.empty_like(t, pin_memory=True).copy_(t)
+    return t.clone()
+
+
 class Invertible:
     """History carrier (data/invertible.py:10-75)."""
 
@@ -264,7 +272,7 @@ class Image(Invertible):
         raise AttributeError(f"{type(self).__name__} has no attribute {name!r}")
 
     def __deepcopy__(self, memo: dict):
-        new = type(self)(self._data.clone(), affine=self._affine.clone(), **self._metadata)
+        new = type(self)(_clone_keeping_pin(self._data), affine=self._affine.clone(), **self._metadata)
         new.applied_transforms = list(self.applied_transforms)
         memo[id(self)] = new
         return new
@@ -425,7 +433,7 @@ class ImagesBatch(Invertible):
 
     def __deepcopy__(self, memo: dict):
         new = type(self)(
-            self._data.clone(), [a.clone() for a in self._affines], image_class=self._image_class
+            _clone_keeping_pin(self._data), [a.clone() for a in self._affines], image_class=self._image_class
         )
         new.applied_transforms = list(self.applied_transforms)
         return new

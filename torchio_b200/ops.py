@@ -81,17 +81,20 @@ class _StagingRing:
         with self.lock:
             i = self.index
             self.index = (i + 1) % self.SLOTS
-        if self.events[i] is not None:
-            self.events[i].synchronize()
+            pending, self.events[i] = self.events[i], None
+        if pending is not None:  # the copy queued behind this slot's previous use
+            pending.synchronize()
         return i, self.buffers[i]
 
     def release(self, i: int, device: torch.device) -> None:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
-        self.events[i] = ev
+        with self.lock:
+            self.events[i] = ev
 
 
 _ring: _StagingRing | None = None
+_init_lock = threading.Lock()
 
 
 def upload(device: torch.device, *arrays):
@@ -116,7 +119,9 @@ def upload(device: torch.device, *arrays):
     slot = None
     if torch.cuda.is_available() and offset <= _StagingRing.SLOT_BYTES:
         if _ring is None:
-            _ring = _StagingRing()
+            with _init_lock:
+                if _ring is None:
+                    _ring = _StagingRing()
         slot, stage = _ring.take()
         stage = stage[:offset]
     else:
@@ -440,8 +445,12 @@ def _mt_table(device: torch.device) -> Tensor:
     key = (device.type, device.index)
     table = _mt_device_tables.get(key)
     if table is None:
-        table = mt19937_host_table().to(device)
-        _mt_device_tables[key] = table
+        with _init_lock:
+            table = _mt_device_tables.get(key)
+            if table is None:
+                table = mt19937_host_table().to(device)
+                torch.cuda.synchronize(device)  # other threads' streams may read it right away
+                _mt_device_tables[key] = table
     return table
 
 

@@ -231,6 +231,37 @@ class LazyParams(dict):
         self._lazy.pop(key, None)
         dict.__setitem__(self, key, value)
 
+    def __iter__(self):
+        # a Python-level __iter__ takes `dict(params)`, `{**params}`, `a | params` and
+        # `other.update(params)` off CPython's raw-storage fast path (dict_merge checks
+        # tp_iter) and onto keys() + __getitem__, which force the lazy entries
+        return dict.__iter__(self)
+
+    def keys(self):
+        return dict.keys(self)
+
+    def pop(self, key, *default):
+        if key in self._lazy:
+            self._force(key)
+        return dict.pop(self, key, *default)
+
+    def popitem(self):
+        self._force()
+        return dict.popitem(self)
+
+    def setdefault(self, key, default=None):
+        if key in self._lazy:
+            self._force(key)
+        return dict.setdefault(self, key, default)
+
+    def __or__(self, other):
+        self._force()
+        return dict(self) | other
+
+    def __ror__(self, other):
+        self._force()
+        return other | dict(self)
+
     def items(self):
         self._force()
         return dict.items(self)

@@ -158,6 +158,11 @@ class Transform(nn.Module):
         of the whole-batch result."""
         return False
 
+    def prepare_stream(self, batch: SubjectsBatch, params: dict[str, Any], cache: dict, step: int) -> None:
+        """Called once on the WHOLE host batch before `Compose` streams it in slices: host tables
+        that depend on more than the slice's own rows (values the reference takes from batch
+        element 0, dispatch decisions over all rows) go into ``cache`` here."""
+
     def _warn_if_noop(self, *, is_noop: bool, hint: str) -> None:
         if is_noop:
             warnings.warn(

@@ -9,6 +9,7 @@ staged to the GPU once for the whole pipeline (not once per child).
 from __future__ import annotations
 
 import copy as _copy
+import threading as _threading
 from collections.abc import Mapping, Sequence
 from typing import Any
 
@@ -18,6 +19,9 @@ from ..data import ImagesBatch, SubjectsBatch
 from ..params import slice_params
 from .base import ChunkInfo, Transform, _Staging, _finish, chunk_scope, execution_device, wrap_input
 from . import intensity as _int
+
+
+_stream_local = _threading.local()
 
 
 class Compose(Transform):
@@ -98,6 +102,9 @@ class Compose(Transform):
         h2d, compute, d2h = streams
         total = batch.batch_size
         cache: dict = {}
+        for step, (_, applied) in enumerate(plan):
+            for transform, params in applied:
+                transform.prepare_stream(batch, params, cache, step)
         names = list(batch.images)
         outputs: dict[str, Any] = {}
         affines: dict[str, list] = {name: [] for name in names}
@@ -149,15 +156,22 @@ class Compose(Transform):
         return batch
 
     def _streams(self, device):
-        cached = self.__dict__.get("_stream_cache")
-        if cached is None or cached[0] != device:
+        """(copy-in, kernels, copy-out) streams of the calling thread for ``device``.  Kept per
+        thread and outside the module's ``__dict__``: a `Queue` calls one Compose from several
+        worker threads (each gets its own triple, so their subjects overlap instead of
+        serialising on shared streams), and the Compose stays picklable / deep-copyable."""
+        cache = getattr(_stream_local, "streams", None)
+        if cache is None:
+            cache = _stream_local.streams = {}
+        key = (device.type, device.index)
+        triple = cache.get(key)
+        if triple is None:
             # the kernel stream also carries the small table uploads of every slice: high
             # priority, or the copy engine serves them only after the queued bulk copies
-            cached = (device, (_torch.cuda.Stream(device=device),
-                               _torch.cuda.Stream(device=device, priority=-1),
-                               _torch.cuda.Stream(device=device)))
-            self.__dict__["_stream_cache"] = cached
-        return cached[1]
+            triple = cache[key] = (_torch.cuda.Stream(device=device),
+                                   _torch.cuda.Stream(device=device, priority=-1),
+                                   _torch.cuda.Stream(device=device))
+        return triple
 
     def _forward_batch(self, batch):
         # Children never copy (compose.py:88-92).  Unlike the reference we do
@@ -226,7 +240,7 @@ def _apply_group(applied, batch) -> None:
                 builders.append(lambda ib, index, p=params: _int._bias_stage(
                     ib.data.shape, ib.affines, p["std"], p["seed"], p["scale"], divide=False))
             elif isinstance(transform, _int.Blur):
-                builders.append(lambda ib, index, p=params: _int._blur_stage(ib, p))
+                builders.append(lambda ib, index, p=params: _int._blur_stage(ib, p, index))
             elif isinstance(transform, _int.Noise):
                 builders.append(_int._noise_stage_factory(params))
             else:

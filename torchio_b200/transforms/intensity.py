@@ -148,13 +148,30 @@ class Blur(IntensityTransform):
         return params
 
     def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
-        run_stages(self._get_images(batch), [lambda ib, index: _blur_stage(ib, params)])
+        run_stages(self._get_images(batch), [lambda ib, index: _blur_stage(ib, params, index)])
         return batch
 
+    def prepare_stream(self, batch: SubjectsBatch, params: dict[str, Any], cache: dict, step: int) -> None:
+        # taps of the whole batch: the mm -> voxel conversion of shared sigmas reads batch element
+        # 0's spacing (blur.py:87), and shared-vs-stacked taps are chosen over ALL rows
+        for index, ib in enumerate(self._get_images(batch).values()):
+            cache[("blur", step, index)] = {"tables": _blur_stage(ib, params, index, whole=True)}
 
-def _blur_stage(ib, params):
+
+def _blur_stage(ib, params, index: int = 0, whole: bool = False):
     """Host tables of the blur stage, or None when every sigma <= 0 (the
-    reference then returns the input tensor itself, blur.py:143-144)."""
+    reference then returns the input tensor itself, blur.py:143-144).  While a batch is streamed
+    in slices the rows come from the whole-batch tables `prepare_stream` cached."""
+    info = None if whole else chunk_info()
+    if info is not None:
+        cached = info.cache.get(("blur", info.step, index))
+        if cached is not None:
+            full = cached["tables"]
+            if full is None:
+                return None
+            return {"taps": full["taps"][:, info.b0:info.b1].contiguous(),
+                    "radius": full["radius"][:, info.b0:info.b1].contiguous(),
+                    "big_r": full["big_r"], "axes_mask": full["axes_mask"]}
     if "_batched_keys" in params:
         mm = np.asarray(params["std"], dtype=np.float64)
         sp = np.asarray([a.spacing for a in ib.affines], dtype=np.float64)
@@ -202,7 +219,13 @@ class Noise(IntensityTransform):
         # counter-based stream indexes voxels of the tensor it is given
         if _noise_mode() != "exact":
             return False
-        return all(int(np.prod(ib.data.shape[1:])) % 16 == 0 for ib in self._get_images(batch).values())
+        images = self._get_images(batch).values()
+        # one stream per application, continued across images and the second Rician draw: all of
+        # it must lie inside the jump table's reach, or the one-shot path (host draws) takes over
+        words = sum(int(np.prod(ib.data.shape)) for ib in images) * (2 if self.rician else 1)
+        if words > ops.MT_MAX_WORDS:
+            return False
+        return all(int(np.prod(ib.data.shape[1:])) % 16 == 0 for ib in images)
 
     def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
         seed = int(torch.randint(0, 2**31, (1,)).item())  # drawn first (noise.py:75)
