@@ -256,19 +256,24 @@ def test_device_queue_uses_the_patch_ring_and_collates_with_one_gather():
         assert torch.equal(h.t1.data, subjects[sid].t1.data[:, i:i + pi, j:j + pj, k:k + pk])
     last = handles[-1]
     assert last.t1.data.data_ptr() == ring.data["t1"][last.slot].data_ptr()  # a view, not a copy
-    # collate: same batches as stacking materialised patches
-    torch.manual_seed(case["seed"])
-    random.seed(case["seed"])
-    loader = tio.SubjectsLoader(queue, batch_size=case["batch_size"])
-    torch.manual_seed(case["seed"])
-    random.seed(case["seed"])
-    reference = tio.SubjectsLoader(_queue(case, _subjects(case, "cpu")), batch_size=case["batch_size"])
+    # collate: same batches as stacking materialised patches (each epoch fully consumed under its
+    # own seeding: the two queues draw from the same global generators)
+    def epoch(q):
+        torch.manual_seed(case["seed"])
+        random.seed(case["seed"])
+        out = []
+        for b in tio.SubjectsLoader(q, batch_size=case["batch_size"]):
+            out.append((b.t1.data.cpu(), b.seg.data.cpu(), [l.index for l in b.metadata["patch_location"]],
+                        list(b.metadata["sid"]), [a.numpy() for a in b.t1.affines]))
+        return out
+
+    got_batches, want_batches = epoch(queue), epoch(_queue(case, _subjects(case, "cpu")))
+    assert len(got_batches) == len(want_batches)
     n = 0
-    for got, want in zip(loader, reference):
-        assert torch.equal(got.t1.data.cpu(), want.t1.data) and torch.equal(got.seg.data.cpu(), want.seg.data)
-        assert [l.index for l in got.metadata["patch_location"]] == [l.index for l in want.metadata["patch_location"]]
-        assert got.metadata["sid"] == want.metadata["sid"]
-        for a, b in zip(got.t1.affines, want.t1.affines):
-            assert np.allclose(a.numpy(), b.numpy(), rtol=0, atol=1e-12)
-        n += got.batch_size
+    for got, want in zip(got_batches, want_batches):
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert got[2] == want[2] and got[3] == want[3]
+        for a, b in zip(got[4], want[4]):
+            assert np.allclose(a, b, rtol=0, atol=1e-12)
+        n += got[0].shape[0]
     assert n == queue.patches_per_epoch
