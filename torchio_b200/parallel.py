@@ -76,9 +76,10 @@ def gather_batch_to_root(batch: SubjectsBatch, *, root: int = 0, counts: list[in
         out = gather_buffers(batch, counts)
     requests = []
     for name in names:
-        data = batch.images[name].data.contiguous()
+        # as bytes: NCCL's point-to-point has no int16 ("Short") and the payload is opaque anyway
+        data = batch.images[name].data.contiguous().view(torch.uint8)
         if rank == root:
-            dest = out[name]
+            dest = out[name].view(torch.uint8)
             for src in range(world):
                 block = dest[offsets[src]:offsets[src + 1]]
                 if src == root:
