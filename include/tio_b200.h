@@ -231,6 +231,33 @@ int tio_gamma(const float* src, float* dst, int B, int64_t per_elem,
               const float* gamma, void* stream);
 
 /*
+ * Data-derived parameters of Standardize / Normalize, computed where the batch lives
+ * (the reference reads batch element 0 on the host: standardize.py:52-79, normalize.py:121-139,
+ * 332-366, _statistics.py:11-45).
+ *   tio_moments    out3 (device doubles) = {sum, sum of squares, count} of the `n` values at `src`
+ *                  for which mask[t] != 0 (mask NULL = all); fp64 accumulation, one pass
+ *   tio_quantiles  for each of the m <= 2 quantiles q (host doubles in [0,1]): index = q*(count-1),
+ *                  lower = floor(index); values[2t], values[2t+1] = the order statistics of rank
+ *                  lower and min(lower+1, count-1) (what torch.kthvalue(lower+1 / lower+2) returns),
+ *                  weights[t] = index - lower, *count = number of selected values.  Exact (3-level
+ *                  radix select over the order-preserving integer image of fp32), three passes.
+ *                  workspace: tio_quantiles_workspace_bytes() device bytes, 16-byte aligned.
+ *   tio_rescale    dst = ((clamp(src, lo, hi) - sub[b]) / div[b]) * mul[b] + add[b] over (B, per_elem),
+ *                  each step rounded to fp32 like the reference's separate elementwise ops
+ *                  (normalize.py:176-181, standardize.py:93; the inverses :271-297, :139-141).
+ *                  `flags` selects the steps: 1 clamp, 2 sub, 4 div, 8 mul, 16 add (tables for
+ *                  unselected steps may be NULL); keep[b] == 0 copies the row.  In-place allowed.
+ */
+int tio_moments(const float* src, const uint8_t* mask, int64_t n, double* out3, void* stream);
+size_t tio_quantiles_workspace_bytes(void);
+int tio_quantiles(const float* src, const uint8_t* mask, int64_t n, const double* q_host, int m,
+                  float* values, double* weights, double* count, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int tio_rescale(const float* src, float* dst, int B, int64_t per_elem, float lo, float hi,
+                const float* sub, const float* div, const float* mul, const float* add,
+                const uint8_t* keep, int flags, void* stream);
+
+/*
  * Fused intensity chain: what Compose([BiasField, Blur, Noise, Gamma]) computes,
  * in two HBM passes.  Any stage may be absent (NULL table / noise_mode 0):
  *   v   = src * exp(trilerp(coarse))   (/ when bias_divide)  if coarse != NULL

@@ -373,6 +373,8 @@ _APPLY = {
     "Spatial": spatial, "Affine": spatial, "ElasticDeformation": spatial,
     "BiasField": bias_field, "Blur": blur, "Noise": noise, "Gamma": gamma,
     "Flip": flip, "Crop": crop, "Pad": pad,
+    # elementwise fp32 maps with recorded constants: the torch restatement is the oracle
+    "Standardize": tp.standardize, "Normalize": tp.normalize,
 }
 
 

@@ -417,6 +417,44 @@ def gamma(images: dict, params: dict, invert: bool = False) -> None:
         img["data"] = x.sign() * x.abs().pow(gam)
 
 
+def standardize(images: dict, params: dict) -> None:
+    """Standardize.apply_transform (intensity/standardize.py:81-94): the recorded (mean, std) of
+    the first sample applied to every element."""
+    for name, img in images.items():
+        if img["kind"] != "scalar" or name not in params["stats"]:
+            continue
+        mean, std = params["stats"][name]
+        if std == 0:
+            raise RuntimeError(f'Standard deviation is zero for masked values in "{name}". Cannot standardize.')
+        img["data"] = (img["data"].float() - mean) / std
+
+
+def normalize(images: dict, params: dict) -> None:
+    """Normalize.apply_transform (intensity/normalize.py:153-183): clamp to the recorded input
+    range, map it onto [out_min, out_max] (per element when the params were sampled per instance)."""
+    for name, img in images.items():
+        if img["kind"] != "scalar":
+            continue
+        if "in_min" in params:
+            in_min, in_max = params["in_min"], params["in_max"]
+        else:
+            if name not in params.get("in_ranges", {}):
+                continue
+            in_min, in_max = params["in_ranges"][name]
+        in_range = in_max - in_min
+        if in_range == 0:
+            continue
+        data = img["data"].float()
+        if isinstance(params["out_min"], list):  # normalize.py:318-326
+            lo = torch.tensor(params["out_min"], dtype=torch.float32, device=data.device).reshape(-1, 1, 1, 1, 1)
+            hi = torch.tensor(params["out_max"], dtype=torch.float32, device=data.device).reshape(-1, 1, 1, 1, 1)
+            out_min, out_range = lo, hi - lo
+        else:
+            out_min, out_range = params["out_min"], params["out_max"] - params["out_min"]
+        data = data.clamp(in_min, in_max)
+        img["data"] = (data - in_min) / in_range * out_range + out_min
+
+
 def flip(images: dict, params: dict) -> None:
     """Flip.apply_transform (spatial/flip.py:186-263): data reversed along the sampled
     axes, per element when params are per-instance; affines untouched."""
@@ -470,6 +508,8 @@ _APPLY = {
     "Blur": blur,
     "Noise": noise,
     "Gamma": gamma,
+    "Standardize": standardize,
+    "Normalize": normalize,
 }
 
 

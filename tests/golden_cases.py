@@ -228,6 +228,27 @@ CALL_CASES = [
          transform=("CropOrPad", {"target_shape": (12, 8, None), "only_pad": True, "fill": 2.5})),
 ]
 
+# ---- data-derived intensity maps: Standardize / Normalize ---------------------
+# Their params hold statistics of batch element 0, so the host-params tests (CPU, kernels stubbed)
+# do not cover them: tests/test_gpu_stats.py checks sampling + statistics + map on the GPU.
+STAT_CASES = [
+    dict(name="standardize_b2", seed=101, shape=(24, 20, 16), batch=2, shift=0.3,
+         images={"t1": "scalar", "seg": "int16"}, transform=("Standardize", {})),
+    dict(name="standardize_masked", seed=102, shape=(24, 20, 16), batch=2, channels=2,
+         images={"t1": "scalar", "seg": "int16"}, transform=("Standardize", {"masking_method": "seg"})),
+    dict(name="normalize_default_b2", seed=103, shape=(24, 20, 16), batch=2, shift=0.3,
+         images={"t1": "scalar", "seg": "int16"}, transform=("Normalize", {})),
+    dict(name="normalize_percentiles", seed=104, shape=(32, 28, 24), batch=2,
+         images={"t1": "scalar"},
+         transform=("Normalize", {"percentile_low": 0.5, "percentile_high": 99.5, "out_min": 0.0, "out_max": 1.0})),
+    dict(name="normalize_random_out_masked", seed=105, shape=(24, 20, 16), batch=3,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Normalize", {"out_min": (-1.0, 0.0), "out_max": (0.5, 1.0), "masking_method": "seg",
+                                  "percentile_low": 1.0, "percentile_high": 99.0})),
+    dict(name="normalize_explicit_in", seed=106, shape=(16, 14, 12), batch=2,
+         images={"t1": "scalar"}, transform=("Normalize", {"in_min": 0.1, "in_max": 0.8})),
+]
+
 # ---- BASELINE.json's own volume size: 256^3 (configs[1] and configs[2], two elements) ----------
 # The reference's full outputs are too large to commit (64 MiB per volume): the fixture keeps
 # a strided lattice of every output, two dense blocks (a corner with padding/fill, the centre),
@@ -257,7 +278,7 @@ def full_views(t):
     }
 
 
-CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES + FULL_CASES}
+CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES + STAT_CASES + FULL_CASES}
 
 
 # ---- patch path: UniformSampler / Queue / SubjectsLoader -------------

@@ -13,7 +13,7 @@ import torch
 from torchio_b200 import _native
 
 ROOT = Path(__file__).resolve().parent.parent
-C2CTYPES = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t}
+C2CTYPES = {"float": ctypes.c_float, "int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t}
 
 
 def header_prototypes():

@@ -16,7 +16,8 @@ from .patches import (GridSampler, ImagesLoader, LabelSampler, PatchLocation, Pa
                       StudiesLoader, SubjectsLoader, UniformSampler, WeightedSampler, collate_images, collate_studies,
                       collate_subjects)
 from .transforms import (Affine, AppliedTransform, BiasField, Blur, Compose, Crop, CropOrPad,
-                         ElasticDeformation, Flip, Gamma, IntensityTransform, Noise, Pad, Spatial, SpatialTransform, Transform,
+                         ElasticDeformation, Flip, Gamma, IntensityTransform, Noise, Normalize, Pad, RescaleIntensity, Spatial,
+                         SpatialTransform, Standardize, Transform,
                          apply_inverse_transform, execution_device, get_inverse_transform,
                          set_execution_device)
 
@@ -25,8 +26,8 @@ __version__ = "0.1.0"
 __all__ = [
     "Affine", "AffineMatrix", "AppliedTransform", "BiasField", "Blur", "Choice", "Compose", "Crop", "CropOrPad",
     "ElasticDeformation", "Flip", "Gamma", "GridSampler", "Image", "ImagesBatch", "ImagesLoader", "IntensityTransform",
-    "LabelMap", "LabelSampler", "Noise", "Pad", "PatchLocation", "PatchSampler", "Queue", "ScalarImage", "Spatial",
-    "SpatialTransform", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
+    "LabelMap", "LabelSampler", "Noise", "Normalize", "Pad", "PatchLocation", "PatchSampler", "Queue", "RescaleIntensity", "ScalarImage", "Spatial",
+    "SpatialTransform", "Standardize", "StudiesBatch", "StudiesLoader", "Subject", "SubjectsBatch",
     "SubjectsLoader", "Transform", "UniformSampler", "WeightedSampler", "apply_inverse_transform", "collate_images",
     "collate_studies", "collate_subjects", "exact_coords_default", "execution_device", "get_inverse_transform",
     "set_exact_coords", "set_execution_device",

@@ -9,7 +9,7 @@ missing or a call fails, a RuntimeError carrying ``tio_last_error()`` is raised.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libtio_b200.so"
@@ -33,6 +33,12 @@ _SIGNATURES = {
     "tio_noise_philox": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                          c_uint64, c_int, c_void_p],
     "tio_gamma": [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p],
+    "tio_moments": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
+    "tio_quantiles_workspace_bytes": [],
+    "tio_quantiles": [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_size_t, c_void_p],
+    "tio_rescale": [c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                    c_void_p, c_int, c_void_p],
     "tio_mt19937_table_bytes": [],
     "tio_mt19937_build_table": [c_void_p, c_size_t],
     "tio_randn_mt19937_workspace_bytes": [c_uint64, c_uint64],

@@ -375,6 +375,71 @@ def gamma(src: Tensor, gam: Tensor) -> Tensor:
     return dst
 
 
+def moments(values: Tensor, mask: Tensor | None = None) -> tuple[float, float, float]:
+    """(sum, sum of squares, count) of the selected values of a contiguous fp32 CUDA tensor, fp64
+    accumulation on the device, one small D2H read (the reference calls ``.item()`` here too:
+    standardize.py:76-77)."""
+    _require_cuda(values, "moments")
+    values = values.contiguous()
+    m8 = None if mask is None else mask.expand_as(values).contiguous().to(torch.uint8)
+    out = torch.empty(3, dtype=torch.float64, device=values.device)
+    with torch.cuda.device(values.device):
+        _native.call("tio_moments", _ptr(values), _ptr(m8), values.numel(), _ptr(out), _stream(values))
+    _count(1)
+    s, ss, n = out.tolist()
+    return s, ss, n
+
+
+def quantile_neighbours(values: Tensor, qs, mask: Tensor | None = None):
+    """For each q in ``qs`` (at most two): the order statistics torch.kthvalue(lower + 1) and
+    kthvalue(lower + 2) return, and ``index - lower`` (transforms/_statistics.py:37-45), found by
+    an exact radix select on the device.  Returns (values[2m], weights[m], count)."""
+    _require_cuda(values, "quantile_neighbours")
+    values = values.contiguous()
+    m8 = None if mask is None else mask.expand_as(values).contiguous().to(torch.uint8)
+    qs = np.ascontiguousarray(np.asarray(qs, dtype=np.float64).reshape(-1))
+    m = int(qs.shape[0])
+    dev = values.device
+    vals = torch.empty(2 * m, dtype=torch.float32, device=dev)
+    out = torch.empty(m + 1, dtype=torch.float64, device=dev)
+    ws_bytes = _native.lib().tio_quantiles_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _native.call("tio_quantiles", _ptr(values), _ptr(m8), values.numel(), qs.ctypes.data, m, _ptr(vals),
+                     _ptr(out), out[m:].data_ptr(), _ptr(ws), ws_bytes, _stream(values))
+    _count(8)
+    host = out.tolist()
+    return vals.tolist(), host[:m], int(host[m])
+
+
+def rescale(src: Tensor, *, lo: float | None = None, hi: float | None = None, sub=None, div=None, mul=None,
+            add=None, keep=None) -> Tensor:
+    """``((clamp(src, lo, hi) - sub[b]) / div[b]) * mul[b] + add[b]`` over a (B, ...) fp32 batch, each
+    step rounded like the reference's separate elementwise ops; omitted steps are skipped.
+    ``sub/div/mul/add``: scalars or length-B sequences; ``keep``: length-B, 0 = copy the row."""
+    _require_cuda(src, "rescale")
+    src = src.contiguous()
+    b = src.shape[0]
+    flags = (1 if lo is not None else 0)
+    tabs = []
+    for bit, table in ((2, sub), (4, div), (8, mul), (16, add)):
+        if table is None:
+            tabs.append(None)
+            continue
+        flags |= bit
+        arr = np.asarray(table, dtype=np.float32).reshape(-1)
+        tabs.append(np.ascontiguousarray(np.broadcast_to(arr, (b,)) if arr.size == 1 else arr))
+    keep_np = None if keep is None else np.ascontiguousarray(np.asarray(keep, dtype=np.uint8))
+    sub_d, div_d, mul_d, add_d, keep_d = upload(src.device, *tabs, keep_np)
+    dst = torch.empty_like(src)
+    with torch.cuda.device(src.device):
+        _native.call("tio_rescale", _ptr(src), _ptr(dst), b, src[0].numel(),
+                     float(lo if lo is not None else 0.0), float(hi if hi is not None else 0.0),
+                     _ptr(sub_d), _ptr(div_d), _ptr(mul_d), _ptr(add_d), _ptr(keep_d), flags, _stream(src))
+    _count(2)
+    return dst
+
+
 def intensity_fused(
     src: Tensor, *, coarse: Tensor | None = None, bias_identity: Tensor | None = None,
     bias_divide: bool = False, taps: Tensor | None = None, radius: Tensor | None = None,

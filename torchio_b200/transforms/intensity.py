@@ -9,6 +9,7 @@ kernels K2-K5 (`torchio_b200.ops`).
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Any
 
 import numpy as np
@@ -372,6 +373,262 @@ class _GammaInverse(IntensityTransform):
         lg = self._log_gamma
         _apply_gamma(self, batch, [-v for v in lg] if isinstance(lg, list) else -lg)
         return batch
+
+
+# ---- Standardize / Normalize (intensity/standardize.py:17-170, normalize.py:35-369) -----------
+#
+# Both read their parameters off batch element 0 (optionally masked) and then apply one affine map
+# to every element.  The statistics run where the data lives (`ops.moments`: fp64 sums in one
+# pass; `ops.quantile_neighbours`: exact radix select instead of torch.kthvalue's sort) and the
+# map is `ops.rescale`, which rounds step by step like the reference's elementwise ops.
+
+
+def _resolve_mask(masking_method, img_batch, batch) -> Tensor | None:
+    """None | LabelMap key | callable -> boolean mask of sample 0 (standardize.py:144-170)."""
+    if masking_method is None:
+        return None
+    if callable(masking_method) and not isinstance(masking_method, str):
+        return masking_method(img_batch.data[0]).bool()
+    if isinstance(masking_method, str):
+        if masking_method not in batch.images:
+            raise KeyError(f'Masking method "{masking_method}" not found in batch images.'
+                           f" Available: {list(batch.images.keys())}")
+        mask_batch = batch.images[masking_method]
+        from ..data import LabelMap
+
+        if not issubclass(mask_batch._image_class, LabelMap):
+            raise TypeError(f'Masking method "{masking_method}" must refer to a LabelMap.')
+        return mask_batch.data[0].bool()
+    raise TypeError(f"masking_method must be None, str, or callable, got {type(masking_method)}")
+
+
+def _sample0(img_batch, mask, warn_empty: str) -> tuple[Tensor, Tensor | None]:
+    """Sample 0 as a contiguous fp32 tensor plus its mask; an empty mask falls back to all voxels
+    with the reference's warning."""
+    tensor = _as_f32(img_batch.data[0]).contiguous()
+    if mask is not None:
+        mask = mask.to(tensor.device).expand_as(tensor)
+        if not bool(mask.any()):
+            warnings.warn(warn_empty, RuntimeWarning, stacklevel=4)
+            mask = None
+    return tensor, mask
+
+
+class Standardize(IntensityTransform):
+    """(v - mean) / std with the statistics of the (masked) first sample (standardize.py:17-107)."""
+
+    def __init__(self, *, masking_method=None, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.masking_method = masking_method
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        stats: dict[str, tuple[float, float]] = {}
+        for name, img_batch in self._get_images(batch).items():
+            mask = _resolve_mask(self.masking_method, img_batch, batch)
+            with _Staged(img_batch) as staged:
+                tensor, mask = _sample0(staged, mask, f'Mask is empty for "{name}". Using all voxels.')
+                s, ss, n = ops.moments(tensor, mask)
+            mean = s / n
+            var = (ss - s * s / n) / (n - 1) if n > 1 else float("nan")  # torch.std: Bessel's correction
+            stats[name] = (float(np.float32(mean)), float(np.float32(np.sqrt(max(var, 0.0)))))
+        return {"stats": stats}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        stats = params["stats"]
+        for name, img_batch in self._get_images(batch).items():
+            if name not in stats:
+                continue
+            mean, std = stats[name]
+            if std == 0:
+                raise RuntimeError(f'Standard deviation is zero for masked values in "{name}".'
+                                   " Cannot standardize.")
+            img_batch.data = ops.rescale(_as_f32(img_batch.data), sub=mean, div=std)
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]) -> _StandardizeInverse:
+        return _StandardizeInverse(stats=params["stats"], copy=False)
+
+
+class _StandardizeInverse(IntensityTransform):
+    def __init__(self, *, stats, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self._stats = stats
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        return {}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        for name, img_batch in self._get_images(batch).items():
+            if name not in self._stats:
+                continue
+            mean, std = self._stats[name]
+            if std == 0:
+                continue
+            img_batch.data = ops.rescale(_as_f32(img_batch.data), mul=std, add=mean)
+        return batch
+
+
+def _lerp_f32(a: float, b: float, weight: float) -> float:
+    """Tensor.lerp(end, weight) on fp32 scalars (ATen: a + w (b - a) below 0.5, b - (b - a)(1 - w) above)."""
+    a32, b32, w32 = np.float32(a), np.float32(b), np.float32(weight)
+    diff = np.float32(b32 - a32)
+    if w32 < np.float32(0.5):
+        return float(np.float32(a32 + np.float32(w32 * diff)))
+    return float(np.float32(b32 - np.float32(diff * np.float32(np.float32(1.0) - w32))))
+
+
+class Normalize(IntensityTransform):
+    """Clip to an input range, then map it linearly onto [out_min, out_max] (normalize.py:35-232)."""
+
+    def __init__(self, *, out_min=-1.0, out_max=1.0, in_min=None, in_max=None, percentile_low=0.0,
+                 percentile_high=100.0, masking_method=None, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self.out_min = _value_range(out_min)
+        self.out_max = _value_range(out_max)
+        self.in_min = _value_range(in_min) if in_min is not None else None
+        self.in_max = _value_range(in_max) if in_max is not None else None
+        self.percentile_low = _value_range(percentile_low)
+        self.percentile_high = _value_range(percentile_high)
+        self.masking_method = masking_method
+
+    @property
+    def supports_per_instance_params(self) -> bool:
+        return True
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        n = self._resolve_n(batch)
+        out_min = self.out_min.sample_1d(n)
+        out_max = self.out_max.sample_1d(n)
+        pct_low = self.percentile_low.sample_1d()
+        pct_high = self.percentile_high.sample_1d()
+        params: dict[str, Any] = {"out_min": self._serialize_param(out_min),
+                                  "out_max": self._serialize_param(out_max)}
+        if self.in_min is not None and self.in_max is not None:
+            params["in_min"] = self.in_min.sample_1d()
+            params["in_max"] = self.in_max.sample_1d()
+        else:
+            in_ranges: dict[str, tuple[float, float]] = {}
+            for name, img_batch in self._get_images(batch).items():
+                mask = _resolve_mask(self.masking_method, img_batch, batch)
+                with _Staged(img_batch) as staged:
+                    tensor, mask = _sample0(staged, mask, f'Cannot compute percentiles for "{name}": mask is'
+                                                          " empty. Using full range.")
+                    values, weights, _ = ops.quantile_neighbours(tensor, [pct_low / 100.0, pct_high / 100.0], mask)
+                low = values[0] if weights[0] == 0 else _lerp_f32(values[0], values[1], weights[0])
+                high = values[2] if weights[1] == 0 else _lerp_f32(values[2], values[3], weights[1])
+                in_ranges[name] = (low, high)
+            params["in_ranges"] = in_ranges
+        if n is not None:
+            self._tag_batched(params, batch, n, None, ["out_min", "out_max"])
+        return params
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        for name, img_batch in self._get_images(batch).items():
+            if "in_min" in params:
+                in_min, in_max = params["in_min"], params["in_max"]
+            else:
+                in_ranges = params.get("in_ranges", {})
+                if name not in in_ranges:
+                    continue
+                in_min, in_max = in_ranges[name]
+            in_range = in_max - in_min
+            if in_range == 0:
+                warnings.warn(f'Cannot rescale "{name}": input range is zero.', RuntimeWarning, stacklevel=2)
+                continue
+            out_min, out_range = _out_min_and_range(params["out_min"], params["out_max"])
+            img_batch.data = ops.rescale(_as_f32(img_batch.data), lo=in_min, hi=in_max, sub=in_min, div=in_range,
+                                         mul=out_range, add=out_min)
+        return batch
+
+    @property
+    def invertible(self) -> bool:
+        return True
+
+    def inverse(self, params: dict[str, Any]) -> _RescaleInverse:
+        return _RescaleInverse(out_min=params["out_min"], out_max=params["out_max"], in_min=params.get("in_min"),
+                               in_max=params.get("in_max"), in_ranges=params.get("in_ranges"), copy=False)
+
+
+RescaleIntensity = Normalize  # the reference's backwards-compatible alias (normalize.py:369)
+
+
+def _value_range(value):
+    if isinstance(value, (int, float)):
+        return to_range(float(value))
+    if isinstance(value, (tuple, list)):
+        return to_range(tuple(float(v) for v in value))
+    return to_range(value)
+
+
+def _out_min_and_range(out_min, out_max):
+    """Scalar pair, or per-element fp32 arrays whose difference is taken in fp32 like the
+    reference's tensors (normalize.py:300-329)."""
+    if isinstance(out_min, list):
+        lo = np.asarray(out_min, dtype=np.float32)
+        return lo, (np.asarray(out_max, dtype=np.float32) - lo).astype(np.float32)
+    return out_min, out_max - out_min
+
+
+class _RescaleInverse(IntensityTransform):
+    def __init__(self, *, out_min, out_max, in_min, in_max, in_ranges, **kwargs: Any) -> None:
+        super().__init__(**kwargs)
+        self._out_min, self._out_max = out_min, out_max
+        self._in_min, self._in_max, self._in_ranges = in_min, in_max, in_ranges
+
+    def make_params(self, batch: SubjectsBatch) -> dict[str, Any]:
+        return {}
+
+    def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
+        for name, img_batch in self._get_images(batch).items():
+            if self._in_min is not None and self._in_max is not None:
+                in_min, in_max = self._in_min, self._in_max
+            elif self._in_ranges is not None and name in self._in_ranges:
+                in_min, in_max = self._in_ranges[name]
+            else:
+                continue
+            in_range = in_max - in_min
+            if in_range == 0:
+                continue
+            out_min, out_range = _out_min_and_range(self._out_min, self._out_max)
+            keep = None
+            if isinstance(out_range, float):
+                if out_range == 0:
+                    continue
+            else:  # per element: rows whose output range was zero stay as they are
+                keep = (out_range != 0).astype(np.uint8)
+                out_range = np.where(out_range == 0, np.float32(1.0), out_range)
+            data = _as_f32(img_batch.data)
+            # (data - out_min) / out_range * in_range + in_min
+            img_batch.data = ops.rescale(data, sub=out_min, div=out_range, mul=in_range, add=in_min, keep=keep)
+        return batch
+
+
+class _Staged:
+    """Sample 0 of an image batch on the execution device for the statistics kernels (make_params
+    runs before `Transform` stages a host batch)."""
+
+    def __init__(self, img_batch) -> None:
+        self.img_batch = img_batch
+
+    def __enter__(self):
+        data = self.img_batch.data
+        if data.is_cuda:
+            return self.img_batch
+        from .base import execution_device
+
+        class _View:
+            pass
+
+        view = _View()
+        view.data = data[:1].to(execution_device(), non_blocking=True)
+        return view
+
+    def __exit__(self, *exc) -> None:
+        return None
 
 
 # ---- shared runner: 1..4 stages -> one fused launch pair per image ---------------
