@@ -100,6 +100,10 @@ def spatial(images, params):
     names = params.get("selected_images", [])
     if not names:
         return
+    if params.get("target") is not None or params.get("antialias", False):
+        # resampling onto another grid / the anti-alias pre-filter: the torch restatement
+        # (F.grid_sample, F.pad + F.conv3d — the reference's own calls) is the oracle
+        return tp.spatial(images, params)
     first = images[names[0]]
     shape = tuple(first["data"].shape[-3:])
     a0 = np.asarray(first["affines"][0], dtype=np.float64)
@@ -370,7 +374,8 @@ def crop_patches(volume, corners, size):
 
 
 _APPLY = {
-    "Spatial": spatial, "Affine": spatial, "ElasticDeformation": spatial,
+    "Spatial": spatial,
+    "Resample": spatial, "Affine": spatial, "ElasticDeformation": spatial,
     "BiasField": bias_field, "Blur": blur, "Noise": noise, "Gamma": gamma,
     "Flip": flip, "Crop": crop, "Pad": pad,
     # elementwise fp32 maps with recorded constants: the torch restatement is the oracle

@@ -160,29 +160,31 @@ def spatial(images: dict, params: dict) -> None:
     names = params.get("selected_images", [])
     if not names:
         return
-    assert params["target"] is None, "oracle covers target=None only"
     per_instance = "affine_matrix" in (params.get("_batched_keys") or [])
     first = images[names[0]]
     shape = tuple(first["data"].shape[-3:])
     a0 = np.asarray(first["affines"][0], dtype=np.float64)
+    target = params["target"]  # {"shape", "affine"} or None (spatial.py:1140-1142)
+    out_shape = shape if target is None else tuple(int(v) for v in target["shape"])
+    a_out = a0 if target is None else np.asarray(target["affine"], dtype=np.float64)
     if per_instance:
         mats = params["affine_matrix"]
         cps = params["control_points"]
-        if all(m is None for m in mats) and all(c is None for c in cps):
+        if target is None and all(m is None for m in mats) and all(c is None for c in cps):
             return
         grids = [
-            sampling_grid(shape, a0, shape, a0, mats[b], cps[b], params["affine_first"])
+            sampling_grid(shape, a0, out_shape, a_out, mats[b], cps[b], params["affine_first"])
             for b in range(len(mats))
         ]
         grid = torch.stack(grids, 0)
-        passthrough = [
+        passthrough = [] if target is not None else [  # spatial.py:1171-1175
             b for b in range(len(mats)) if mats[b] is None and cps[b] is None
         ]
     else:
         mat, cp = params["affine_matrix"], params["control_points"]
-        if mat is None and cp is None:
+        if target is None and mat is None and cp is None:
             return
-        grid = sampling_grid(shape, a0, shape, a0, mat, cp, params["affine_first"])
+        grid = sampling_grid(shape, a0, out_shape, a_out, mat, cp, params["affine_first"])
         passthrough = []
     for name in names:
         img = images[name]
@@ -195,16 +197,60 @@ def spatial(images: dict, params: dict) -> None:
         fill = fill_value_for(
             data, img["kind"], params["default_pad_value"], params["default_pad_label"]
         )
-        out = grid_sample_with_fill(data, grid, shape, mode, fill)
+        source = data
+        if params.get("antialias", False) and img["kind"] != "label":  # spatial.py:1256-1257
+            source = antialias(data, a0, a_out)
+        out = grid_sample_with_fill(source, grid, shape, mode, fill)
         if passthrough:
             out = out.contiguous()
             for b in passthrough:  # spatial.py:1101-1106
                 out[b] = data[b]
         img["data"] = out
         img["affines"] = [
-            img["affines"][b] if b in passthrough else a0.copy()
+            img["affines"][b] if b in passthrough else a_out.copy()
             for b in range(len(img["affines"]))
         ]
+
+
+def antialias_sigmas(factors, spacing):
+    """Cardoso et al. (MICCAI 2015) sigma in voxels per downsampled axis (spatial.py:1951-1978)."""
+    sigmas = np.zeros(3, dtype=np.float64)
+    for axis in range(3):
+        k = factors[axis]
+        if k <= 1.0:
+            continue
+        variance = (k**2 - 1) * (2 * np.sqrt(2 * np.log(2))) ** (-2)
+        sigma_mm = spacing[axis] * np.sqrt(variance)
+        sigmas[axis] = sigma_mm / spacing[axis]
+    return sigmas
+
+
+def antialias(data, a_in, a_out):
+    """_antialias_batch + _gaussian_smooth_batch (spatial.py:1921-2031): replicate pad + conv3d per
+    downsampled axis with one shared kernel."""
+    sp_in = np.asarray(spacing_of(a_in), dtype=np.float64)
+    sigmas = antialias_sigmas(np.asarray(spacing_of(a_out), dtype=np.float64) / sp_in, sp_in)
+    if np.all(sigmas == 0):
+        return data
+    result = data.float()
+    b, c = result.shape[:2]
+    for axis in range(3):
+        sigma = float(sigmas[axis])
+        if sigma <= 0:
+            continue
+        radius = max(int(np.ceil(3 * sigma)), 1)
+        x = torch.arange(2 * radius + 1, dtype=torch.float32, device=data.device) - radius
+        k = torch.exp(-0.5 * (x / sigma) ** 2)
+        k = k / k.sum()
+        k_shape = [1, 1, 1]
+        k_shape[axis] = 2 * radius + 1
+        pad = [0] * 6
+        pad[2 * (2 - axis)] = radius
+        pad[2 * (2 - axis) + 1] = radius
+        padded = F.pad(result, pad, mode="replicate")
+        result = F.conv3d(padded.reshape(b * c, 1, *padded.shape[2:]), k.reshape(1, 1, *k_shape), padding=0)
+        result = result.reshape(b, c, *result.shape[2:])
+    return result.to(data.dtype)
 
 
 # ----------------------------------------------------------------------------
@@ -502,6 +548,7 @@ _APPLY = {
     "Crop": crop,
     "Pad": pad,
     "Spatial": spatial,
+    "Resample": spatial,
     "Affine": spatial,
     "ElasticDeformation": spatial,
     "BiasField": bias_field,

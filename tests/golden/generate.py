@@ -29,7 +29,7 @@ sys.path.insert(2, str(HERE.parent))
 
 import torchio as tio  # noqa: E402  (the reference)
 
-from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES, STAT_CASES, build_inputs  # noqa: E402
+from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES, RESAMPLE_CASES, STAT_CASES, build_inputs  # noqa: E402
 
 
 def _make_transform(spec):
@@ -76,8 +76,8 @@ def main():
     torch.set_num_threads(1)
     out_dir = HERE
     only = sys.argv[1] if len(sys.argv) > 1 else "all"   # "neighbours": leave the hot-path fixtures alone
-    selected = {"neighbours": NEIGHBOUR_CASES, "call": CALL_CASES, "stats": STAT_CASES}.get(
-        only, CASES + NEIGHBOUR_CASES + CALL_CASES + STAT_CASES)
+    selected = {"neighbours": NEIGHBOUR_CASES, "call": CALL_CASES, "stats": STAT_CASES,
+                "resample": RESAMPLE_CASES}.get(only, CASES + NEIGHBOUR_CASES + CALL_CASES + STAT_CASES + RESAMPLE_CASES)
     for case in selected:
         arrays = run_case(case)
         path = out_dir / f"{case['name']}.npz"

@@ -249,6 +249,25 @@ STAT_CASES = [
          images={"t1": "scalar"}, transform=("Normalize", {"in_min": 0.1, "in_max": 0.8})),
 ]
 
+# ---- remaining Spatial modes: target spaces, anti-aliasing -------------------
+_TARGET_AFFINE = [[0.0, -1.3, 0.0, 14.0], [1.1, 0.0, 0.0, -3.0], [0.0, 0.0, 1.6, 2.0], [0.0, 0.0, 0.0, 1.0]]
+RESAMPLE_CASES = [
+    dict(name="resample_iso2_aniso", seed=111, shape=(20, 18, 14), batch=2, spacing=(0.8, 1.1, 2.0),
+         origin=(-7.0, 3.5, 10.0), tilt=0.1, images={"t1": "scalar", "seg": "int16"},
+         transform=("Resample", {"target": 2})),
+    dict(name="resample_antialias_down", seed=112, shape=(24, 20, 16), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Resample", {"target": (2.0, 2.5, 3.0), "antialias": True})),
+    dict(name="resample_up_half", seed=113, shape=(12, 10, 8), batch=1,
+         images={"t1": "scalar", "seg": "uint8"}, transform=("Resample", {"target": 0.5})),
+    dict(name="resample_random_spacing", seed=114, shape=(20, 18, 14), batch=2,
+         images={"t1": "scalar"}, transform=("Resample", {"target": (1.5, 2.5), "antialias": True})),
+    dict(name="spatial_target_space_affine", seed=115, shape=(18, 16, 14), batch=2, spacing=(1.2, 0.9, 1.5),
+         images={"t1": "scalar", "seg": "uint8"},
+         transform=("Spatial", {**_AFF, "max_displacement": (1.0, 2.5), "num_control_points": 6,
+                                "target": ((14, 20, 12), _TARGET_AFFINE)})),
+]
+
 # ---- BASELINE.json's own volume size: 256^3 (configs[1] and configs[2], two elements) ----------
 # The reference's full outputs are too large to commit (64 MiB per volume): the fixture keeps
 # a strided lattice of every output, two dense blocks (a corner with padding/fill, the centre),
@@ -278,7 +297,8 @@ def full_views(t):
     }
 
 
-CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES + STAT_CASES + FULL_CASES}
+CASES_BY_NAME = {c["name"]: c for c in CASES + NEIGHBOUR_CASES + CALL_CASES + STAT_CASES + RESAMPLE_CASES
+                 + FULL_CASES}
 
 
 # ---- patch path: UniformSampler / Queue / SubjectsLoader -------------

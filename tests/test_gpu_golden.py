@@ -11,20 +11,20 @@ import copy
 import pytest
 import torch
 
-from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES
+from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES, RESAMPLE_CASES
 from util import load_golden, product_batch, product_replay, report
 
 pytestmark = pytest.mark.gpu
 
 TOL_RANGE = 1e-4
-SPATIAL = {"Affine", "ElasticDeformation", "Spatial"}
+SPATIAL = {"Affine", "ElasticDeformation", "Spatial", "Resample"}
 
 
 # fast coordinates: the reference's own coordinate noise (<= ~2e-5 voxel) times the local gradient
 TOL_FAST_VS_ORACLE = 1e-4
 
 
-@pytest.mark.parametrize("name", [c["name"] for c in CASES])
+@pytest.mark.parametrize("name", [c["name"] for c in CASES + RESAMPLE_CASES])
 def test_cuda_matches_reference_golden(name, coords):
     from oracle import c_port
 

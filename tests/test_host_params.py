@@ -7,7 +7,7 @@ import warnings
 import pytest
 import torch
 
-from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES
+from golden_cases import CALL_CASES, CASES, NEIGHBOUR_CASES, RESAMPLE_CASES
 from util import load_golden, make_product_transform, product_batch
 
 
@@ -30,7 +30,7 @@ def _sample_only(transform, batch, monkeypatch, fuse):
 @pytest.mark.parametrize("fuse", [False, True])
 # (kernels are stubbed here, so a pipeline whose later params depend on an earlier shape
 # change is checked through the real call on the GPU instead: test_gpu_golden.py)
-@pytest.mark.parametrize("name", [c["name"] for c in CASES + NEIGHBOUR_CASES
+@pytest.mark.parametrize("name", [c["name"] for c in CASES + NEIGHBOUR_CASES + RESAMPLE_CASES
                                   if c["name"] != "compose_flip_pad_affine_crop"])
 def test_params_match_reference(name, fuse, monkeypatch):
     """Sequential and Compose-fused execution draw the same RNG stream."""

@@ -10,12 +10,12 @@ import copy
 import pytest
 import torch
 
-from golden_cases import CASES, NEIGHBOUR_CASES, STAT_CASES
+from golden_cases import CASES, NEIGHBOUR_CASES, RESAMPLE_CASES, STAT_CASES
 from oracle import torch_port
 from util import load_golden, report
 
 
-@pytest.mark.parametrize("name", [c["name"] for c in CASES + NEIGHBOUR_CASES + STAT_CASES])
+@pytest.mark.parametrize("name", [c["name"] for c in CASES + NEIGHBOUR_CASES + STAT_CASES + RESAMPLE_CASES])
 def test_torch_port_matches_reference_golden(name):
     _, images, history, expected, expected_aff = load_golden(name)
     out = torch_port.replay(copy.deepcopy(images), history)

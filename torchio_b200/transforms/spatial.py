@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import warnings
 from numbers import Number
+from pathlib import Path
 from typing import Any
 
 import numpy as np
@@ -28,7 +29,7 @@ from torch.distributions import Distribution
 
 from .. import ops, tables
 from ..data import AffineMatrix, Image, ImagesBatch, LabelMap, SubjectsBatch
-from ..params import Choice, LazyParams, _ParameterRange, uniform_from_unit
+from ..params import Choice, LazyParams, _ParameterRange, to_range, uniform_from_unit
 from .base import SpatialTransform, chunk_info
 
 _ORDERS = {
@@ -266,19 +267,101 @@ def _space_from_json(d):
 
 
 def _resolve_target(target, batch, shape, affine):
+    """User-facing ``target`` -> ``(shape, affine)`` or None (spatial.py:1392-1422): an Image, a
+    ``(shape, affine)`` pair, the name of an image of the subject, or a spacing specification
+    (scalar, 3 values, or anything `_ParameterRange` samples: ranges, Choice, Distribution — drawn
+    here, after the geometry, as upstream)."""
     if target is None:
         return None
     if isinstance(target, Image):
         return tuple(target.spatial_shape), target.affine.clone()
+    if isinstance(target, (str, Path)):
+        if isinstance(target, str) and target in batch.images:
+            reference = batch.images[target]
+            return _shape_of(reference), reference.affines[0].clone()
+        if Path(target).is_file():
+            raise NotImplementedError("torchio_b200 reads no image files: pass the target Image or (shape, affine)")
+        raise ValueError(f'Unknown target "{target}". Pass a file path, an image name in the'
+                         " subject, an Image, or a spacing specification")
     if isinstance(target, tuple) and len(target) == 2 and not isinstance(target[0], Number):
         s, a = target
         if len(s) != 3:
             raise ValueError(f"Target shape must have length 3, got {len(s)}")
         return (int(s[0]), int(s[1]), int(s[2])), AffineMatrix(a)
-    raise NotImplementedError(
-        "torchio_b200.Spatial supports target=None, an Image or a (shape, affine) pair;"
-        " spacing / random / named targets are not implemented yet"
-    )
+    if not isinstance(target, (int, float, tuple, list, np.ndarray, Choice, Distribution)):
+        raise ValueError(f'Target not understood: "{target}"')
+    return _space_for_spacing(shape, affine, _resolve_target_spacing(target))
+
+
+def _parse_spacing(value) -> tuple[float, float, float]:
+    """Strictly positive 3-tuple (spatial.py:2566-2587)."""
+    if isinstance(value, (int, float)):
+        spacing = (float(value),) * 3
+    else:
+        flat = [float(v) for v in (value.flat if isinstance(value, np.ndarray) else value)]
+        if len(flat) != 3:
+            kind = "Spacing array" if isinstance(value, np.ndarray) else "Spacing"
+            raise ValueError(f"{kind} must have 3 values, got {len(flat)}")
+        spacing = (flat[0], flat[1], flat[2])
+    if any(v <= 0 for v in spacing):
+        raise ValueError(f"Spacing must be strictly positive, got {spacing}")
+    return spacing
+
+
+def _resolve_target_spacing(value) -> tuple[float, float, float]:
+    """spatial.py:1445-1469: deterministic for scalars / arrays, else one `_ParameterRange` draw."""
+    if isinstance(value, np.ndarray):
+        return _parse_spacing(value)
+    if isinstance(value, (int, float)):
+        return _parse_spacing(float(value))
+    spec = tuple(value) if isinstance(value, list) else value
+    return _parse_spacing(to_range(spec).sample())
+
+
+def _space_for_spacing(shape, affine: AffineMatrix, spacing):
+    """Output grid of a new voxel spacing: same physical centre, ``floor(shape * old / new)``
+    voxels, singleton axes kept (spatial.py:1472-1501)."""
+    old_spacing = np.asarray(affine.spacing, dtype=np.float64)
+    new_spacing = np.asarray(spacing, dtype=np.float64)
+    old_shape = np.asarray(shape, dtype=np.float64)
+    new_shape = np.floor(old_shape * old_spacing / new_spacing)
+    new_shape[old_shape == 1] = 1
+    rotation = np.asarray(affine.direction, dtype=np.float64)
+    old_center = np.asarray(affine.origin, dtype=np.float64) + rotation @ (((old_shape - 1) / 2) * old_spacing)
+    new_origin = old_center - rotation @ (((new_shape - 1) / 2) * new_spacing)
+    matrix = np.eye(4, dtype=np.float64)
+    matrix[:3, :3] = rotation * new_spacing
+    matrix[:3, 3] = new_origin
+    return (int(new_shape[0]), int(new_shape[1]), int(new_shape[2])), AffineMatrix(matrix)
+
+
+def _antialias_sigmas(factors, spacing) -> np.ndarray:
+    """Per-axis sigma in voxels for the axes that are downsampled (Cardoso et al., MICCAI 2015;
+    spatial.py:1951-1978, same float64 operation order)."""
+    sigmas = np.zeros(3, dtype=np.float64)
+    for axis in range(3):
+        k = factors[axis]
+        if k <= 1.0:
+            continue
+        variance = (k**2 - 1) * (2 * np.sqrt(2 * np.log(2))) ** (-2)
+        sigma_mm = spacing[axis] * np.sqrt(variance)
+        sigmas[axis] = sigma_mm / spacing[axis]
+    return sigmas
+
+
+def _antialias(data, a_in: AffineMatrix, a_out: AffineMatrix):
+    """Gaussian pre-filter of `_antialias_batch` (spatial.py:1921-1948): one shared set of taps,
+    replicate padding, through the blur kernels of the intensity path (K3)."""
+    input_spacing = np.asarray(a_in.spacing, dtype=np.float64)
+    factors = np.asarray(a_out.spacing, dtype=np.float64) / input_spacing
+    sigmas = _antialias_sigmas(factors, input_spacing)
+    if np.all(sigmas == 0):
+        return data
+    t = tables.blur_tables([float(v) for v in sigmas], data.shape[0])
+    taps, radius = ops.upload(data.device, t.taps, t.radius)
+    native = data if data.dtype == torch.float32 else data.float()
+    out = ops.blur(native, taps, radius, t.big_r, t.axes_mask, None)
+    return out if out.dtype == data.dtype else out.to(data.dtype)
 
 
 # ---- the transform -----------------------------------------------------------
@@ -653,8 +736,6 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
                    max_displacements=None) -> None:
     if not names:
         return
-    if antialias:
-        raise NotImplementedError("antialias=True is not implemented in torchio_b200")
     mats, cps, per_instance = geometry
     first = batch.images[names[0]]
     in_shape, a_in = _shape_of(first), first.affines[0]
@@ -690,6 +771,8 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
             info.cache[("fill", info.step, name)] = fill
         else:
             fill = info.cache[("fill", info.step, name)]
+        if antialias and not is_label:  # after the fill value (spatial.py:1249-1257): blur what is downsampled
+            native = _antialias(native, a_in, a_out)
         out = ops.resample(
             native, mat_d, cp_d, flags_d, a_in.spacing, a_out.spacing,
             affine_first=affine_first, mode=ops.NEAREST if interp == "nearest" else ops.LINEAR,
@@ -729,6 +812,17 @@ def _box_hint(packed, sp_in, sp_out, out_shape) -> int:
         if worst <= edge:
             return edge
     return 32
+
+
+class Resample(Spatial):
+    """Resampling-only wrapper: ``Resample(2)`` = 2 mm isotropic, ``Resample("t1")`` = the space of
+    that image, ``Resample((1, 1, 3))`` (spatial.py:759-803)."""
+
+    def __init__(self, target=1, image_interpolation="linear", label_interpolation="nearest",
+                 one_hot_label_interpolation="linear", antialias: bool = False, **kwargs: Any) -> None:
+        super().__init__(target=target, image_interpolation=image_interpolation,
+                         label_interpolation=label_interpolation,
+                         one_hot_label_interpolation=one_hot_label_interpolation, antialias=antialias, **kwargs)
 
 
 class Affine(Spatial):
