@@ -33,7 +33,8 @@ def test_cuda_matches_reference_golden(name, coords):
     out = product_replay(batch, history)
     torch.cuda.synchronize()
     oracle = c_port.replay(copy.deepcopy(images), history)
-    only_spatial = all(h["name"] in SPATIAL for h in history)
+    # (the anti-alias pre-filter is a blur: conv summation order, not a pure gather)
+    only_spatial = all(h["name"] in SPATIAL and not h["params"].get("antialias") for h in history)
     for n, exp in expected.items():
         got = out.images[n].data.cpu()
         assert got.dtype == exp.dtype and got.shape == exp.shape

@@ -70,7 +70,9 @@ def _make(name, **kw):
 @pytest.mark.parametrize("spec", [
     ("Blur", {"std": (0.5, 2.0)}), ("BiasField", {"std": (0.3, 0.8)}),
     ("Flip", {"axes": (0, 1, 2), "flip_probability": 0.5}), ("Gamma", {"log_gamma": (-0.3, 0.3)}),
-    ("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10)}), ("ElasticDeformation", {"max_displacement": 2.0}),
+    # (a numeric pad value: "minimum" is defined by sample 0 of whatever batch the transform sees)
+    ("Affine", {"scales": (0.9, 1.1), "degrees": (-10, 10), "default_pad_value": 0.5}),
+    ("ElasticDeformation", {"max_displacement": 2.0, "default_pad_value": 0.5}),
 ], ids=lambda s: s[0])
 def test_vectorized_matches_per_element(spec):
     torch.manual_seed(0)
@@ -80,7 +82,7 @@ def test_vectorized_matches_per_element(spec):
 @pytest.mark.parametrize("spec", [
     ("Blur", {"std": 1.5, "p": 0.5}), ("BiasField", {"std": 0.5, "p": 0.5}),
     ("Flip", {"axes": (0, 1, 2), "flip_probability": 1.0, "p": 0.5}), ("Gamma", {"log_gamma": 0.3, "p": 0.5}),
-    ("Affine", {"degrees": (-10, 10), "p": 0.5}),
+    ("Affine", {"degrees": (-10, 10), "p": 0.5, "default_pad_value": 0.5}),
 ], ids=lambda s: s[0])
 def test_vectorized_matches_per_element_with_gating(spec):
     torch.manual_seed(0)
