@@ -24,6 +24,7 @@
 // resample_common.cuh, so fill decisions stay bit-exact.  Label maps, nearest interpolation
 // and TIO_EXACT_COORDS launches use resample_tile.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "resample_tile.cuh"
 
@@ -319,40 +320,64 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     char* out_b = out_a + ostride * (long long)sizeof(float);
     const float fill_c = masked ? a.fill[c] : 0.0f;
     f2 rel2 = pack2(0.0f, 1.0f);
-    auto pair = [&](const int p) {
-      if (HAS_CP && ((mask >> p) & 1u)) {  // CTA-uniform: a plane of this pair enters a new control cell
-        float aa[3], ab[3], ba[3], bb[3];
-        const int cell_a = cell_tab[2 * p], cell_b = cell_tab[2 * p + 1];
-        cell_constants(cell_a, aa, ba);
-        if (cell_b != cell_a) {
-          cell_constants(cell_b, ab, bb);
-        } else {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) { ab[ax] = aa[ax]; bb[ax] = ba[ax]; }
+    // pairs [p, p + count) with the column constants as they are; MASKED resolved outside
+    auto run = [&](const int p0, const int count, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll 2
+      for (int q = 0; q < count; ++q) {
+        float va, vb;
+        bool unc_a = false, unc_b = false;
+        pair_step<C1, C2, MASKED>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
+        *reinterpret_cast<float*>(out_a) = va;
+        *reinterpret_cast<float*>(out_b) = vb;
+        if (MASKED) {
+          if (unc_a) unsafe |= 1u << (2 * (p0 + q));
+          if (unc_b) unsafe |= 2u << (2 * (p0 + q));
         }
-        A0 = pack2(aa[0], ab[0]); A1 = pack2(aa[1], ab[1]); A2 = pack2(aa[2], ab[2]);
-        B0 = pack2(ba[0], bb[0]); B1 = pack2(ba[1], bb[1]); B2 = pack2(ba[2], bb[2]);
+        out_a += pair_bytes; out_b += pair_bytes;
+        rel2 = add2(rel2, bc(2.0f));
       }
-      float va, vb;
-      bool unc_a = false, unc_b = false;
-      if (masked) pair_step<C1, C2, true>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
-      else pair_step<C1, C2, false>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
-      *reinterpret_cast<float*>(out_a) = va;
-      *reinterpret_cast<float*>(out_b) = vb;
-      if (HAS_FILL) {
-        if (unc_a) unsafe |= 1u << (2 * p);
-        if (unc_b) unsafe |= 2u << (2 * p);
-      }
-      out_a += pair_bytes; out_b += pair_bytes;
-      rel2 = add2(rel2, bc(2.0f));
     };
     if constexpr (HAS_CP) {
-      // one copy of the body: the cell set-up inlined eight times thrashed the instruction cache
-#pragma unroll 1
-      for (int p = 0; p < XT / 2; ++p) pair(p);
+      // segments of pairs that share their control cells (CTA-uniform): the cell set-up runs
+      // between segments, the walk inside a segment is the plain loop
+      int p = 0;
+      while (p < XT / 2) {
+        if ((mask >> p) & 1u) {
+          float aa[3], ab[3], ba[3], bb[3];
+          const int cell_a = cell_tab[2 * p], cell_b = cell_tab[2 * p + 1];
+          cell_constants(cell_a, aa, ba);
+          if (cell_b != cell_a) {
+            cell_constants(cell_b, ab, bb);
+          } else {
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) { ab[ax] = aa[ax]; bb[ax] = ba[ax]; }
+          }
+          A0 = pack2(aa[0], ab[0]); A1 = pack2(aa[1], ab[1]); A2 = pack2(aa[2], ab[2]);
+          B0 = pack2(ba[0], bb[0]); B1 = pack2(ba[1], bb[1]); B2 = pack2(ba[2], bb[2]);
+        }
+        const unsigned later = (mask >> (p + 1)) << (p + 1);  // next pair that changes cells
+        const int stop = later ? __ffs(later) - 1 : XT / 2;
+        if (masked) run(p, stop - p, std::true_type{});
+        else run(p, stop - p, std::false_type{});
+        p = stop;
+      }
     } else {
 #pragma unroll
-      for (int p = 0; p < XT / 2; ++p) pair(p);
+      for (int p = 0; p < XT / 2; ++p) {
+        float va, vb;
+        bool unc_a = false, unc_b = false;
+        if (masked) pair_step<C1, C2, true>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
+        else pair_step<C1, C2, false>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
+        *reinterpret_cast<float*>(out_a) = va;
+        *reinterpret_cast<float*>(out_b) = vb;
+        if (HAS_FILL) {
+          if (unc_a) unsafe |= 1u << (2 * p);
+          if (unc_b) unsafe |= 2u << (2 * p);
+        }
+        out_a += pair_bytes; out_b += pair_bytes;
+        rel2 = add2(rel2, bc(2.0f));
+      }
     }
   }
   // voxels on the fill threshold again, all channels, with the exact chain and global-memory

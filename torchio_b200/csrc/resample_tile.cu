@@ -643,10 +643,10 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
   // per-tile records live in caller-provided workspace: no allocation, no state kept
   if (!workspace || workspace_bytes < (size_t)n_tiles * sizeof(int4) || ((uintptr_t)workspace & 15)) return 1;
   int4* records = (int4*)workspace;
-  const unsigned bounds_blocks = (unsigned)((n_tiles + 7) / 8);
+  const unsigned bounds_blocks = (unsigned)((n_tiles + 127) / 128);
   if (mode == TIO_NEAREST && !fast) return 1;
-  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, bk, records);
-  else tile_bounds_kernel<false><<<bounds_blocks, 256, 0, st>>>(a, box, kalign, bk, records);
+  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, records);
+  else tile_bounds_kernel<false><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, records);
   const size_t smem = ((size_t)box * box * bk * esize + 15) / 16 * 16 + kAuxFloats * sizeof(float);
   if (mode == TIO_NEAREST) {
     if (dtype == TIO_U8) launch_nearest<uint8_t>(box, tm, a, ta, grid, smem, records, st);

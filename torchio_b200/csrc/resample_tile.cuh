@@ -121,21 +121,26 @@ __device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts
 //   bit 11: the output tile is a full 16^3 (no ragged edge)
 // ---------------------------------------------------------------------------
 template <bool HAS_CP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const int bk, int4* __restrict__ records) {
-  const int lane = threadIdx.x & 31;
+  // ONE THREAD per tile: the work of a tile is a short serial chain (index arithmetic, a dozen
+  // table loads, interval arithmetic); a warp per tile left 31 lanes idle and made the pass
+  // latency-bound at 14 waves of warps per SM (0.055 / 0.155 ms per 32 x 256^3 launch).
   const int tiles_i = (a.OI + XT - 1) / XT, tiles_j = (a.OJ + XT - 1) / XT, tiles_k = (a.OK + XT - 1) / XT;
   const int64_t n_tiles = (int64_t)a.B * tiles_i * tiles_j * tiles_k;
-  const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= n_tiles) return;
-  const int tk = (int)(tile % tiles_k), tj = (int)((tile / tiles_k) % tiles_j);
-  const int ti = (int)((tile / ((int64_t)tiles_k * tiles_j)) % tiles_i);
-  const int b = (int)(tile / ((int64_t)tiles_k * tiles_j * tiles_i));
+  const unsigned per_b = (unsigned)(tiles_i * tiles_j * tiles_k);
+  const int b = (int)(tile / per_b);
+  unsigned rest = (unsigned)(tile - (int64_t)b * per_b);
+  const int tk = (int)(rest % (unsigned)tiles_k);
+  rest /= (unsigned)tiles_k;
+  const int tj = (int)(rest % (unsigned)tiles_j), ti = (int)(rest / (unsigned)tiles_j);
   const int i0 = ti * XT, j0 = tj * XT, k0 = tk * XT;
   const int i1 = min(i0 + XT, a.OI) - 1, j1 = min(j0 + XT, a.OJ) - 1, k1 = min(k0 + XT, a.OK) - 1;
   const uint8_t fl = a.flags ? a.flags[b] : 0;
   if (fl & TIO_FLAG_PASSTHROUGH) {
-    if (lane == 0) records[tile] = make_int4(0, 0, 0, 3);
+    records[tile] = make_int4(0, 0, 0, 3);
     return;
   }
   const bool elastic = HAS_CP && (fl & TIO_FLAG_ELASTIC);
@@ -152,24 +157,16 @@ tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const 
     } else {
 #pragma unroll
       for (int ax = 0; ax < 3; ++ax) { dmn[ax] = 3.0e38f; dmx[ax] = -3.0e38f; }
-      const int total = ni_ * nj_ * nk_;
-      for (int t = lane; t < total; t += 32) {
-        const int qk = t % nk_, qj = (t / nk_) % nj_, qi = t / (nk_ * nj_);
-        float d[3];
-        disp_at(g, a, pi[qi], pj[qj], pk[qk], d);
+      for (int qi = 0; qi < ni_; ++qi)
+        for (int qj = 0; qj < nj_; ++qj)
+          for (int qk = 0; qk < nk_; ++qk) {
+            float d[3];
+            disp_at(g, a, pi[qi], pj[qj], pk[qk], d);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) { dmn[ax] = fminf(dmn[ax], d[ax]); dmx[ax] = fmaxf(dmx[ax], d[ax]); }
-      }
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1)
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          dmn[ax] = fminf(dmn[ax], __shfl_xor_sync(0xffffffffu, dmn[ax], s));
-          dmx[ax] = fmaxf(dmx[ax], __shfl_xor_sync(0xffffffffu, dmx[ax], s));
-        }
+            for (int ax = 0; ax < 3; ++ax) { dmn[ax] = fminf(dmn[ax], d[ax]); dmx[ax] = fmaxf(dmx[ax], d[ax]); }
+          }
     }
   }
-  if (lane != 0) return;
   const float* m = a.mat + b * 12;
   const int dims[3] = {a.I, a.J, a.K};
   const float plo[3] = {(float)i0, (float)j0, (float)k0};
