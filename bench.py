@@ -337,7 +337,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": launches,
         "host_issue_ms_per_step": host_issue_ms,
         "roofline": {
-            "kernel": "resample_kernel (K1, %d launches in the timed region)" % len(k1_ms),
+            "kernel": "K1 = tile_bounds_kernel + resample_fast_kernel (%d launches in the timed region)" % len(k1_ms),
             "bound": "hbm",
             "achieved": achieved,
             "peak": peak,
@@ -348,6 +348,7 @@ def run_b200(args, rank, world, local_rank):
             "avg_launch_ms": k1_avg_ms,
             "share_of_step": sum(k1_ms) / ms if k1_ms else None,
             "traffic": k1_traffic(args),
+            "traffic_source": "profiles/r2_k1_traffic.json (committed ncu --set full capture, not this run)",
         },
         "clocks": clocks,
     }
@@ -582,9 +583,10 @@ def gpu_reference(args, dev):
 
 
 def k1_traffic(args):
-    """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this
-    workload (profiles/r1_k1_traffic.json), or None when the run differs from it."""
-    path = ROOT / "profiles" / "r1_k1_traffic.json"
+    """DRAM bytes per K1 launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the affine and
+    the elastic launch) from the committed `ncu --set full` capture of this workload
+    (profiles/r2_k1_traffic.json) — not re-measured in this run — or None when the run differs."""
+    path = ROOT / "profiles" / "r2_k1_traffic.json"
     if not path.exists() or args.batch != 32 or args.size != VOL:
         return None
     return json.loads(path.read_text()).get("bytes_per_launch")

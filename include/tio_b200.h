@@ -73,7 +73,7 @@ int tio_abi_version(void);
  *   spacing_in/out  host float[3]: fp32 casts of the affine column norms
  *              (spatial.py:1559-1568)
  *   affine_first    spatial.py:1570-1577
- *   mode       TIO_NEAREST | TIO_LINEAR (spatial.py:150-153)
+ *   mode       TIO_NEAREST | TIO_LINEAR (spatial.py:150-153), optionally | TIO_EXACT_COORDS
  *   fill       [C] fp32 per-channel fill, or NULL = skip the mask step
  *              (the reference skips it only for a python-float 0.0 fill,
  *              spatial.py:2072-2076).  The mask is always the TRILINEAR

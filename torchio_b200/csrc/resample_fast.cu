@@ -157,13 +157,17 @@ __device__ __forceinline__ void pair_step(const f2 rel2, const f2 A0, const f2 A
 
 template <int BOX, bool HAS_CP, bool HAS_FILL, int LK>
 __global__ void __launch_bounds__(256, BOX <= 22 ? 4 : 3)
-resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ResampleArgs a,
-                     const __grid_constant__ TileArgs ta,
+resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_s,
+                     const __grid_constant__ ResampleArgs a, const __grid_constant__ TileArgs ta,
                      const int4* __restrict__ records) {
   constexpr int BK = box_k_extent(BOX, 4);
   constexpr int NBOX = BOX * BOX * BK;
   constexpr int BOXBYTES = (NBOX * 4 + 15) / 16 * 16;
   constexpr int C1 = BOX * BK, C2 = BK;
+  // elastic launches: tiles whose pre-image fits the small box load that instead (bit 12)
+  constexpr bool DUAL = HAS_CP && BOX > kSmallBox;
+  constexpr int BKS = box_k_extent(kSmallBox, 4);
+  constexpr int NBOXS = kSmallBox * kSmallBox * BKS, C1S = kSmallBox * BKS, C2S = BKS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* aux = reinterpret_cast<float*>(smem_raw + BOXBYTES);
   const uint32_t box_u32 = smem_u32(smem_raw);
@@ -184,11 +188,12 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     slow_tile<HAS_CP, HAS_FILL>(a, ta, rec, b, i0, j0, k0);
     return;
   }
+  const bool small = DUAL && (rec.w & 4096);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(bar, (uint32_t)(NBOX * 4));
-    tma_load_4d(box_u32, &tmap, rec.z, rec.y, rec.x, b * a.C, bar);
+    mbar_expect_tx(bar, (uint32_t)((small ? NBOXS : NBOX) * 4));
+    tma_load_4d(box_u32, small ? &tmap_s : &tmap, rec.z, rec.y, rec.x, b * a.C, bar);
   }
   const bool elastic = HAS_CP && (rec.w & 1024);
   const bool masked = HAS_FILL && !(rec.w & 256);  // some tap of the tile may leave the volume
@@ -310,8 +315,8 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     if (c > 0) {
       __syncthreads();  // every thread is done with the previous channel's box
       if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)(NBOX * 4));
-        tma_load_4d(box_u32, &tmap, rec.z, rec.y, rec.x, b * a.C + c, bar);
+        mbar_expect_tx(bar, (uint32_t)((small ? NBOXS : NBOX) * 4));
+        tma_load_4d(box_u32, small ? &tmap_s : &tmap, rec.z, rec.y, rec.x, b * a.C + c, bar);
         mbar_wait(bar, (uint32_t)(c & 1));
       }
       __syncthreads();
@@ -321,13 +326,15 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     const float fill_c = masked ? a.fill[c] : 0.0f;
     f2 rel2 = pack2(0.0f, 1.0f);
     // pairs [p, p + count) with the column constants as they are; MASKED resolved outside
-    auto run = [&](const int p0, const int count, auto masked_tag) {
+    auto run = [&](const int p0, const int count, auto masked_tag, auto small_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
+      constexpr bool SMALL = decltype(small_tag)::value;
 #pragma unroll 2
       for (int q = 0; q < count; ++q) {
         float va, vb;
         bool unc_a = false, unc_b = false;
-        pair_step<C1, C2, MASKED>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
+        pair_step<SMALL ? C1S : C1, SMALL ? C2S : C2, MASKED>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb,
+                                                                unc_a, unc_b);
         *reinterpret_cast<float*>(out_a) = va;
         *reinterpret_cast<float*>(out_b) = vb;
         if (MASKED) {
@@ -358,8 +365,13 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         }
         const unsigned later = (mask >> (p + 1)) << (p + 1);  // next pair that changes cells
         const int stop = later ? __ffs(later) - 1 : XT / 2;
-        if (masked) run(p, stop - p, std::true_type{});
-        else run(p, stop - p, std::false_type{});
+        if (small) {
+          if (masked) run(p, stop - p, std::true_type{}, std::true_type{});
+          else run(p, stop - p, std::false_type{}, std::true_type{});
+        } else {
+          if (masked) run(p, stop - p, std::true_type{}, std::false_type{});
+          else run(p, stop - p, std::false_type{}, std::false_type{});
+        }
         p = stop;
       }
     } else {
@@ -386,47 +398,47 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 }
 
 template <int BOX, bool HAS_CP, int LK>
-static void launch_fast_lk(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
-                           size_t smem, const int4* records, cudaStream_t st) {
+static void launch_fast_lk(const CUtensorMap& tm, const CUtensorMap& tms, const ResampleArgs& a, const TileArgs& ta,
+                           dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
   if (a.fill) {
     cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, true, LK>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_fast_kernel<BOX, HAS_CP, true, LK><<<grid, 256, smem, st>>>(tm, a, ta, records);
+    resample_fast_kernel<BOX, HAS_CP, true, LK><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
   } else {
     cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, false, LK>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_fast_kernel<BOX, HAS_CP, false, LK><<<grid, 256, smem, st>>>(tm, a, ta, records);
+    resample_fast_kernel<BOX, HAS_CP, false, LK><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
   }
 }
 
 template <int BOX>
-static void launch_fast(const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
-                        size_t smem, int lk, const int4* records, cudaStream_t st) {
+static void launch_fast(const CUtensorMap& tm, const CUtensorMap& tms, const ResampleArgs& a, const TileArgs& ta,
+                        dim3 grid, size_t smem, int lk, const int4* records, cudaStream_t st) {
   if (a.cp) {
-    if (lk == 4) launch_fast_lk<BOX, true, 4>(tm, a, ta, grid, smem, records, st);
-    else if (lk == 8) launch_fast_lk<BOX, true, 8>(tm, a, ta, grid, smem, records, st);
-    else launch_fast_lk<BOX, true, 16>(tm, a, ta, grid, smem, records, st);
+    if (lk == 4) launch_fast_lk<BOX, true, 4>(tm, tms, a, ta, grid, smem, records, st);
+    else if (lk == 8) launch_fast_lk<BOX, true, 8>(tm, tms, a, ta, grid, smem, records, st);
+    else launch_fast_lk<BOX, true, 16>(tm, tms, a, ta, grid, smem, records, st);
   } else {
-    if (lk == 4) launch_fast_lk<BOX, false, 4>(tm, a, ta, grid, smem, records, st);
-    else if (lk == 8) launch_fast_lk<BOX, false, 8>(tm, a, ta, grid, smem, records, st);
-    else launch_fast_lk<BOX, false, 16>(tm, a, ta, grid, smem, records, st);
+    if (lk == 4) launch_fast_lk<BOX, false, 4>(tm, tms, a, ta, grid, smem, records, st);
+    else if (lk == 8) launch_fast_lk<BOX, false, 8>(tm, tms, a, ta, grid, smem, records, st);
+    else launch_fast_lk<BOX, false, 16>(tm, tms, a, ta, grid, smem, records, st);
   }
 }
 
 // fp32 + trilinear tiles of the launch prepared by launch_resample_tile (tensor map, tile
 // arguments, bounds records); TIO_B200_K1_LK = 16 | 8 | 4 picks the lane layout (development knob)
-void launch_resample_fast(int box, const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
-                          size_t smem, const int4* records, cudaStream_t st) {
+void launch_resample_fast(int box, const CUtensorMap& tm, const CUtensorMap& tm_small, const ResampleArgs& a,
+                          const TileArgs& ta, dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
   static const int lk = []() {
     const char* e = getenv("TIO_B200_K1_LK");
     const int v = e ? atoi(e) : 16;
     return (v == 4 || v == 8) ? v : 16;
   }();
-  if (box == 20) launch_fast<20>(tm, a, ta, grid, smem, lk, records, st);
-  else if (box == 22) launch_fast<22>(tm, a, ta, grid, smem, lk, records, st);
-  else if (box == 24) launch_fast<24>(tm, a, ta, grid, smem, lk, records, st);
-  else if (box == 28) launch_fast<28>(tm, a, ta, grid, smem, lk, records, st);
-  else launch_fast<32>(tm, a, ta, grid, smem, lk, records, st);
+  if (box == 20) launch_fast<20>(tm, tm_small, a, ta, grid, smem, lk, records, st);
+  else if (box == 22) launch_fast<22>(tm, tm_small, a, ta, grid, smem, lk, records, st);
+  else if (box == 24) launch_fast<24>(tm, tm_small, a, ta, grid, smem, lk, records, st);
+  else if (box == 28) launch_fast<28>(tm, tm_small, a, ta, grid, smem, lk, records, st);
+  else launch_fast<32>(tm, tm_small, a, ta, grid, smem, lk, records, st);
 }
 
 }  // namespace tio

@@ -556,7 +556,8 @@ static void launch_box(const CUtensorMap& tm, const ResampleArgs& a, const TileA
   }
 }
 
-void launch_resample_fast(int box, const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta, dim3 grid,
+void launch_resample_fast(int box, const CUtensorMap& tm, const CUtensorMap& tm_small, const ResampleArgs& a,
+                          const TileArgs& ta, dim3 grid,
                           size_t smem, const int4* records, cudaStream_t st);  // resample_fast.cu
 
 // nearest-neighbour label maps: the admitted-division variants only (else the caller's
@@ -645,8 +646,20 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
   int4* records = (int4*)workspace;
   const unsigned bounds_blocks = (unsigned)((n_tiles + 127) / 128);
   if (mode == TIO_NEAREST && !fast) return 1;
-  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, records);
-  else tile_bounds_kernel<false><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, records);
+  // elastic launches of the fast kernel: most tiles need far less than the launch's box (the
+  // displacement is smooth, its borders are locked) and load a small box instead
+  const bool dual = !exact_coords && mode == TIO_LINEAR && a.cp && box > kSmallBox;
+  const int box_s = dual ? kSmallBox : 0, bk_s = dual ? box_k_extent(kSmallBox, 4) : 0;
+  CUtensorMap tm_small = tm;
+  if (dual) {
+    const cuuint32_t bdim_s[4] = {(cuuint32_t)bk_s, (cuuint32_t)box_s, (cuuint32_t)box_s, 1};
+    if (encode(&tm_small, ttype, 4, const_cast<void*>(a.src), gdim, gstride, bdim_s, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 1;
+  }
+  if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, box_s, bk_s, records);
+  else tile_bounds_kernel<false><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, box_s, bk_s, records);
   const size_t smem = ((size_t)box * box * bk * esize + 15) / 16 * 16 + kAuxFloats * sizeof(float);
   if (mode == TIO_NEAREST) {
     if (dtype == TIO_U8) launch_nearest<uint8_t>(box, tm, a, ta, grid, smem, records, st);
@@ -655,7 +668,7 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
     return 0;
   }
   if (!exact_coords) {  // fp32 images: one-fma coordinates where no tap can leave the volume
-    launch_resample_fast(box, tm, a, ta, grid, smem, records, st);
+    launch_resample_fast(box, tm, tm_small, a, ta, grid, smem, records, st);
     return 0;
   }
   if (box == 20) launch_box<20>(tm, a, ta, grid, smem, fast, records, st);

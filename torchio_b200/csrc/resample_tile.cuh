@@ -10,6 +10,7 @@
 namespace tio {
 
 constexpr int XT = 16;  // output tile edge
+constexpr int kSmallBox = 18;  // second, smaller box of elastic fast-kernel launches
 // inner (K) extent of the staged box in elements: BOX plus room for rounding the origin down
 // to a 16-byte boundary, itself rounded up so that a box row is a multiple of 16 bytes
 // (cuTensorMapEncodeTiled rejects other inner extents: BOX = 22 fp32 needs 28, not 26)
@@ -119,10 +120,12 @@ __device__ __forceinline__ int axis_points(float scale, int lo, int hi, int* pts
 //   code 2: pre-image entirely outside the volume    code 3: pass-through element
 //   bit 8: every tap in bounds   bit 9: identity matrix   bit 10: elastic element
 //   bit 11: the output tile is a full 16^3 (no ragged edge)
+//   bit 12: the pre-image also fits the small box (box_s x box_s x bk_s) of the fast kernel
 // ---------------------------------------------------------------------------
 template <bool HAS_CP>
 __global__ void __launch_bounds__(128)
-tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const int bk, int4* __restrict__ records) {
+tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const int bk, const int box_s,
+                   const int bk_s, int4* __restrict__ records) {
   // ONE THREAD per tile: the work of a tile is a short serial chain (index arithmetic, a dozen
   // table loads, interval arithmetic); a warp per tile left 31 lanes idle and made the pass
   // latency-bound at 14 waves of warps per SM (0.055 / 0.155 ms per 32 x 256^3 launch).
@@ -184,6 +187,7 @@ tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const 
     }
   }
   bool fits = ok_bounds, interior = true, outside = false;
+  bool fits_small = ok_bounds && box_s > 0;  // also fits the small box of the fast kernel (bit 12)
   int ilo[3];
 #pragma unroll
   for (int ax = 0; ax < 3; ++ax) {
@@ -206,6 +210,7 @@ tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const 
     if (hi < 0 || lo > dims[ax] - 1) outside = true;
     if (ax == 2) lo &= ~(kalign - 1);  // TMA: innermost coordinate must be 16-byte aligned
     if (hi - lo + 1 > (ax == 2 ? bk : box)) fits = false;
+    if (hi - lo + 1 > (ax == 2 ? bk_s : box_s)) fits_small = false;
     if (lo < 0 || hi > dims[ax] - 1) interior = false;
     ilo[ax] = lo;
   }
@@ -215,7 +220,8 @@ tile_bounds_kernel(const ResampleArgs a, const int box, const int kalign, const 
                      m[10] == 1.f && m[11] == 0.f;  // [p,1] @ I^T == p exactly
   const bool full = (i0 + XT <= a.OI) && (j0 + XT <= a.OJ) && (k0 + XT <= a.OK);
   records[tile] = make_int4(ilo[0], ilo[1], ilo[2], code | (interior ? 256 : 0) | (ident ? 512 : 0) |
-                                                        (elastic ? 1024 : 0) | (full ? 2048 : 0));
+                                                        (elastic ? 1024 : 0) | (full ? 2048 : 0) |
+                                                        ((fits && fits_small) ? 4096 : 0));
 }
 
 struct LiEntry {  // per output plane of the tile: I-axis lerp of the control grid
