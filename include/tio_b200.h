@@ -42,7 +42,7 @@ enum tio_dtype {
   TIO_I64 = 5
 };
 
-enum tio_interp { TIO_NEAREST = 0, TIO_LINEAR = 1 };
+enum tio_interp { TIO_NEAREST = 0, TIO_LINEAR = 1, TIO_LABEL_PV = 2 };
 /* OR into `mode`: keep the reference's fp32 rounding sequence of the sampling coordinates on
  * every tile.  Without it, fp32 trilinear tiles whose taps all lie inside the volume evaluate the
  * same mapping with one fma per axis (differs from the reference's own coordinate noise by
@@ -73,7 +73,14 @@ int tio_abi_version(void);
  *   spacing_in/out  host float[3]: fp32 casts of the affine column norms
  *              (spatial.py:1559-1568)
  *   affine_first    spatial.py:1570-1577
- *   mode       TIO_NEAREST | TIO_LINEAR (spatial.py:150-153), optionally | TIO_EXACT_COORDS
+ *   mode       TIO_NEAREST | TIO_LINEAR (spatial.py:150-153), optionally | TIO_EXACT_COORDS;
+ *              TIO_LABEL_PV = label_interpolation="label" with the default linear one-hot
+ *              interpolation, fused (spatial.py:1275-1389 without materialising the one-hot
+ *              channels): C must be 1, fill[0] = default_pad_label (required); per output voxel
+ *              the trilinear weight of every label among the 8 taps is accumulated in
+ *              grid_sample's corner order, the largest wins (smallest label on ties, as
+ *              argmax over torch.unique's ascending channels), and voxels whose in-bounds
+ *              weight is not > 0.5 take the pad label.  Any dtype; general gather kernel.
  *   fill       [C] fp32 per-channel fill, or NULL = skip the mask step
  *              (the reference skips it only for a python-float 0.0 fill,
  *              spatial.py:2072-2076).  The mask is always the TRILINEAR
@@ -99,6 +106,21 @@ int tio_resample(const void* src, void* dst, int dtype,
                  const float* spacing_in, const float* spacing_out,
                  int affine_first, int mode, const float* fill, int box_hint,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The materialised form of label_interpolation="label", for the combinations the fused mode
+ * does not cover (antialias=True blurs the one-hot channels before they are sampled,
+ * spatial.py:1367-1368):
+ *   tio_onehot        dst (B, n, vox) fp32 = (src (B, vox) == labels[c])  (spatial.py:1362-1365);
+ *                     `labels` = the n distinct values of the batch, ascending, as device
+ *                     int64 (integer dtypes) or fp32 (TIO_F32) values
+ *   tio_label_argmax  dst (B, vox) of `dtype` = labels[argmax_c sampled (B, n, vox)] (first maximum),
+ *                     or pad_label where the sequential channel sum is not > 0.5 (spatial.py:1378-1389)
+ */
+int tio_onehot(const void* src, int dtype, int B, int64_t vox, const void* labels, int n,
+               float* dst, void* stream);
+int tio_label_argmax(const float* sampled, int B, int n, int64_t vox, const void* labels,
+                     float pad_label, void* dst, int dtype, void* stream);
 
 /*
  * Patch extraction for the Queue path: gathers `n` patches of size (pi,pj,pk) with

@@ -151,6 +151,28 @@ def fill_value_for(data, kind, pad_value, pad_label):
     )
 
 
+def label_partial_volume(data, vox, in_shape, a_in, a_out, antialias_on, one_hot_mode, pad_label):
+    """``label_interpolation="label"`` (spatial.py:1275-1389): one-hot per distinct value,
+    optional anti-alias blur, per-channel sampling with zero padding, argmax, pad label where
+    the channel sum is not > 0.5.  C > 1: the channels are sampled without re-encoding."""
+    if data.shape[1] > 1:
+        smoothed = data.float()
+        if antialias_on:
+            smoothed = antialias(smoothed, a_in, a_out)
+        sampled = grid_sample_with_fill(smoothed, vox, in_shape, one_hot_mode, 0.0)
+        return sampled.to(data.dtype) if data.dtype.is_floating_point else sampled
+    labels = torch.unique(data)
+    one_hot = (data[:, 0][:, None] == labels.reshape(1, -1, 1, 1, 1)).float()
+    if antialias_on:
+        one_hot = antialias(one_hot, a_in, a_out)
+    sampled = grid_sample_with_fill(one_hot, vox, in_shape, one_hot_mode, 0.0)
+    winners = sampled.argmax(dim=1)
+    resampled = labels[winners]
+    in_bounds = sampled.sum(dim=1) > 0.5
+    resampled = torch.where(in_bounds, resampled, torch.full_like(resampled, pad_label))
+    return resampled[:, None].to(data.dtype)
+
+
 def spatial(images: dict, params: dict) -> None:
     """Spatial.apply_transform with target=None (spatial.py:560-610,1110-1272).
 
@@ -194,6 +216,20 @@ def spatial(images: dict, params: dict) -> None:
             if img["kind"] == "label"
             else params["image_interpolation"]
         )
+        if img["kind"] == "label" and mode == "label":
+            out = label_partial_volume(
+                data, grid, shape, a0, a_out, params.get("antialias", False),
+                params.get("one_hot_label_interpolation", "linear"), float(params["default_pad_label"]))
+            if passthrough:
+                out = out.contiguous()
+                for b in passthrough:
+                    out[b] = data[b]
+            img["data"] = out
+            img["affines"] = [
+                img["affines"][b] if b in passthrough else a_out.copy()
+                for b in range(len(img["affines"]))
+            ]
+            continue
         fill = fill_value_for(
             data, img["kind"], params["default_pad_value"], params["default_pad_label"]
         )

@@ -266,6 +266,26 @@ RESAMPLE_CASES = [
          images={"t1": "scalar", "seg": "uint8"},
          transform=("Spatial", {**_AFF, "max_displacement": (1.0, 2.5), "num_control_points": 6,
                                 "target": ((14, 20, 12), _TARGET_AFFINE)})),
+    # label_interpolation="label" (partial-volume one-hot / argmax, spatial.py:1275-1389)
+    dict(name="label_pv_affine", seed=116, shape=(20, 17, 13), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Affine", {**_AFF, "label_interpolation": "label", "default_pad_label": 3})),
+    dict(name="label_pv_elastic_gated", seed=117, shape=(18, 16, 14), batch=4, spacing=(1.2, 0.9, 1.5),
+         images={"seg": "int32"},
+         transform=("Spatial", {**_AFF, "max_displacement": (1.0, 2.5), "num_control_points": 6,
+                                "label_interpolation": "label", "default_pad_label": 9, "p": 0.6})),
+    # axis-aligned down/up-sampling: exact half-voxel positions, i.e. argmax ties everywhere
+    dict(name="label_pv_resample_down", seed=118, shape=(20, 18, 14), batch=2,
+         images={"t1": "scalar", "seg": "uint8"},
+         transform=("Resample", {"target": 2, "label_interpolation": "label"})),
+    dict(name="label_pv_resample_up", seed=119, shape=(12, 10, 8), batch=1,
+         images={"seg": "int64"}, transform=("Resample", {"target": 0.5, "label_interpolation": "label"})),
+    dict(name="label_pv_antialias", seed=120, shape=(24, 20, 16), batch=2,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Resample", {"target": (2.0, 2.5, 3.0), "antialias": True, "label_interpolation": "label"})),
+    dict(name="label_pv_onehot_nearest", seed=121, shape=(16, 14, 12), batch=2,
+         images={"seg": "uint8"},
+         transform=("Affine", {**_AFF, "label_interpolation": "label", "one_hot_label_interpolation": "nearest"})),
 ]
 
 # ---- BASELINE.json's own volume size: 256^3 (configs[1] and configs[2], two elements) ----------

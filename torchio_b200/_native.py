@@ -39,6 +39,8 @@ _SIGNATURES = {
                       c_size_t, c_void_p],
     "tio_rescale": [c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_int, c_void_p],
+    "tio_onehot": [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p],
+    "tio_label_argmax": [c_void_p, c_int, c_int, c_int64, c_void_p, c_float, c_void_p, c_int, c_void_p],
     "tio_mt19937_table_bytes": [],
     "tio_mt19937_build_table": [c_void_p, c_size_t],
     "tio_randn_mt19937_workspace_bytes": [c_uint64, c_uint64],

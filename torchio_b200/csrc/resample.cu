@@ -89,6 +89,17 @@ static int launch_typed(const ResampleArgs& a, int mode, cudaStream_t st) {
     TIO_SET_SMEM((resample_kernel<T, TIO_LINEAR, true, false>))
   }
 #undef TIO_SET_SMEM
+  if (mode == TIO_LABEL_PV) {  // fill[0] is the pad label: always present
+    if (has_cp) {
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(resample_kernel<T, TIO_LABEL_PV, true, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      resample_kernel<T, TIO_LABEL_PV, true, true><<<grid, block, smem, st>>>(a);
+    } else {
+      resample_kernel<T, TIO_LABEL_PV, false, true><<<grid, block, smem, st>>>(a);
+    }
+    return 0;
+  }
   if (mode == TIO_NEAREST) {
     if (has_cp) return launch_fill<T, TIO_NEAREST, true>(a, grid, block, smem, st);
     return launch_fill<T, TIO_NEAREST, false>(a, grid, block, smem, st);
@@ -159,7 +170,9 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
                 "tio_resample: non-positive shape");
   const bool exact_coords = (mode & TIO_EXACT_COORDS) != 0;
   mode &= ~TIO_EXACT_COORDS;
-  TIO_CHECK_ARG(mode == TIO_NEAREST || mode == TIO_LINEAR, "tio_resample: bad mode %d", mode);
+  TIO_CHECK_ARG(mode == TIO_NEAREST || mode == TIO_LINEAR || mode == TIO_LABEL_PV, "tio_resample: bad mode %d", mode);
+  TIO_CHECK_ARG(mode != TIO_LABEL_PV || (C == 1 && fill),
+                "tio_resample: TIO_LABEL_PV needs C == 1 and fill[0] = the pad label");
   TIO_CHECK_ARG(spacing_in && spacing_out, "tio_resample: null spacing");
   TIO_CHECK_ARG(!cp || (ni >= 2 && nj >= 2 && nk >= 2), "tio_resample: control grid < 2 per axis");
   TIO_CHECK_ARG((int64_t)B * ((OI + TI - 1) / TI) <= 65535 && (OJ + TJ - 1) / TJ <= 65535,
@@ -182,7 +195,7 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   a.affine_first = affine_first;
   a.cp_in_smem = cp && ((size_t)ni * nj * nk * 12 <= 96 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
-  if (box_hint >= 0) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
+  if (box_hint >= 0 && mode != TIO_LABEL_PV) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
     const int rc = launch_resample_tile(a, dtype, mode, exact_coords, box_hint, workspace, workspace_bytes, st);
     if (rc == 0) {
       TIO_CHECK_LAUNCH();

@@ -147,7 +147,7 @@ __device__ __forceinline__ void general_column(const ResampleArgs& a, const int 
 
     float w[8];
     bool inb[8];
-    bool need_w = (MODE == TIO_LINEAR) || (HAS_FILL && !interior);
+    bool need_w = (MODE != TIO_NEAREST) || (HAS_FILL && !interior);
     if (need_w) {
       // ATen: weight_lo = (c+1) - u, weight_hi = u - c  (exact ints as floats)
       float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u[0]), hi0 = __fsub_rn(u[0], f0);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void general_column(const ResampleArgs& a, const int 
       inb[6] = i_lo & j_hi & k_hi; inb[7] = i_hi & j_hi & k_hi;
     }
     bool use_fill = false;
-    if (HAS_FILL && !interior) {
+    if (MODE != TIO_LABEL_PV && HAS_FILL && !interior) {
       float msum = 0.0f;
 #pragma unroll
       for (int t = 0; t < 8; ++t)
@@ -193,6 +193,41 @@ __device__ __forceinline__ void general_column(const ResampleArgs& a, const int 
         else v = ok_in ? __ldg(src + c * n_in + off) : (T)0;
         dst[c * n_out + o_off] = v;
       }
+    } else if (MODE == TIO_LABEL_PV) {
+      // Partial-volume label resampling (spatial.py:1275-1389, C == 1): one-hot per label value,
+      // trilinear sample of every channel (zero padding, no mask step: the sampler is called with
+      // a python-float 0.0 fill), argmax over the channels in ascending label order (first
+      // maximum wins), default_pad_label where the channel sum is not > 0.5.  A one-hot channel
+      // sampled by grid_sample is the sum, in corner order, of the weights of the corners that
+      // carry its label (1 * w and + 0 * w are exact), so only the labels of the 8 taps matter:
+      // every other channel is exactly 0 and can neither win nor move the sum.
+      const int64_t base = ((int64_t)c0 * a.J + c1) * a.K + c2;
+      const int64_t sI = (int64_t)a.J * a.K, sJ = a.K;
+      T tap[8];
+      unsigned todo = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const bool act = interior || inb[t];
+        tap[t] = act ? __ldg(src + base + (t & 1) * sI + ((t >> 1) & 1) * sJ + ((t >> 2) & 1)) : (T)0;
+        todo |= act ? (1u << t) : 0u;
+      }
+      const unsigned active = todo;
+      float total = 0.0f, best_s = -1.0f;
+      T best = (T)0;
+      while (todo) {
+        T lab = (T)0;
+        bool have = false;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (((todo >> t) & 1u) && (!have || tap[t] < lab)) { lab = tap[t]; have = true; }
+        float s = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (((active >> t) & 1u) && tap[t] == lab) { s = __fadd_rn(s, w[t]); todo &= ~(1u << t); }
+        total = __fadd_rn(total, s);  // sampled.sum(dim=1): ascending label order
+        if (s > best_s) { best_s = s; best = lab; }
+      }
+      dst[o_off] = (total > 0.5f) ? best : ElemTraits<T>::from_f32(a.fill[0]);
     } else {
       const int64_t base = ((int64_t)c0 * a.J + c1) * a.K + c2;
       const int64_t sI = (int64_t)a.J * a.K, sJ = a.K;

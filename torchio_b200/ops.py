@@ -22,7 +22,7 @@ DTYPE_CODES = {
     torch.float32: 0, torch.uint8: 1, torch.int8: 2,
     torch.int16: 3, torch.int32: 4, torch.int64: 5,
 }
-NEAREST, LINEAR = 0, 1
+NEAREST, LINEAR, LABEL_PV = 0, 1, 2
 FLAG_PASSTHROUGH, FLAG_ELASTIC = 1, 2
 
 _counter = threading.local()
@@ -215,6 +215,46 @@ def resample(
             _ptr(fill), int(box_hint), _ptr(workspace), ws_bytes, _stream(src),
         )
     _count(2 if workspace is not None else 1)
+    return dst
+
+
+def _label_table(labels: Tensor, dtype: torch.dtype) -> Tensor:
+    return labels.to(torch.float32 if dtype == torch.float32 else torch.int64).contiguous()
+
+
+def onehot(src: Tensor, labels: Tensor) -> Tensor:
+    """(B,1,I,J,K) label batch -> (B,n,I,J,K) fp32 one-hot channels, ``labels`` = the distinct
+    values in ascending order (spatial/spatial.py:1362-1365)."""
+    _require_cuda(src, "onehot")
+    if src.dtype not in DTYPE_CODES:
+        raise TypeError(f"onehot: unsupported dtype {src.dtype}")
+    src = src.contiguous()
+    b, n = src.shape[0], int(labels.numel())
+    vox = src[0].numel()
+    table = _label_table(labels, src.dtype)
+    dst = torch.empty((b, n, *src.shape[2:]), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _native.call("tio_onehot", _ptr(src), DTYPE_CODES[src.dtype], b, vox, _ptr(table), n, _ptr(dst),
+                     _stream(src))
+    _count(1)
+    return dst
+
+
+def label_argmax(sampled: Tensor, labels: Tensor, pad_label: float, dtype: torch.dtype) -> Tensor:
+    """(B,n,I,J,K) sampled one-hot channels -> (B,1,I,J,K) labels of ``dtype``: first maximum over
+    the channels, ``pad_label`` where their sum is not > 0.5 (spatial/spatial.py:1378-1389)."""
+    _require_cuda(sampled, "label_argmax")
+    if dtype not in DTYPE_CODES:
+        raise TypeError(f"label_argmax: unsupported dtype {dtype}")
+    sampled = sampled.contiguous()
+    b, n = sampled.shape[:2]
+    vox = sampled[0, 0].numel()
+    table = _label_table(labels, dtype)
+    dst = torch.empty((b, 1, *sampled.shape[2:]), dtype=dtype, device=sampled.device)
+    with torch.cuda.device(sampled.device):
+        _native.call("tio_label_argmax", _ptr(sampled), b, n, vox, _ptr(table), float(pad_label), _ptr(dst),
+                     DTYPE_CODES[dtype], _stream(sampled))
+    _count(1)
     return dst
 
 

@@ -640,6 +640,7 @@ class Spatial(SpatialTransform):
             image_interpolation=params["image_interpolation"],
             label_interpolation=params["label_interpolation"],
             antialias=params.get("antialias", False),
+            one_hot_label_interpolation=params.get("one_hot_label_interpolation", "linear"),
             default_pad_value=params["default_pad_value"],
             default_pad_label=float(params["default_pad_label"]),
         )
@@ -664,6 +665,7 @@ class Spatial(SpatialTransform):
             affine_first=not params["affine_first"],
             image_interpolation=params["image_interpolation"],
             label_interpolation=params["label_interpolation"],
+            one_hot_label_interpolation=params.get("one_hot_label_interpolation", "linear"),
             default_pad_value=params["default_pad_value"],
             default_pad_label=float(params["default_pad_label"]),
             copy=False, include=params["selected_images"],
@@ -689,8 +691,10 @@ class _SpatialInverse(SpatialTransform):
     """Concrete inverse used by history replay (spatial.py:679-756)."""
 
     def __init__(self, *, target, geometry, affine_first, image_interpolation,
-                 label_interpolation, default_pad_value, default_pad_label, **kwargs: Any):
+                 label_interpolation, default_pad_value, default_pad_label,
+                 one_hot_label_interpolation="linear", **kwargs: Any):
         super().__init__(**kwargs)
+        self.one_hot_label_interpolation = one_hot_label_interpolation
         self.target = target
         self.geometry = geometry
         self.affine_first = affine_first
@@ -704,6 +708,7 @@ class _SpatialInverse(SpatialTransform):
             batch, list(self._get_images(batch)), self.target, self.geometry,
             affine_first=self.affine_first, image_interpolation=self.image_interpolation,
             label_interpolation=self.label_interpolation, antialias=False,
+            one_hot_label_interpolation=self.one_hot_label_interpolation,
             default_pad_value=self.default_pad_value, default_pad_label=self.default_pad_label,
         )
         return batch
@@ -731,9 +736,42 @@ def _fill_tensor(data: Tensor, is_label: bool, pad_value, pad_label):
     return torch.full((c,), value, dtype=torch.float32, device=data.device)
 
 
+def _resample_label_pv(data, resample, *, antialias, a_in, a_out, one_hot_interpolation, pad_label):
+    """``label_interpolation="label"`` (spatial.py:1275-1389).  ``resample(tensor, mode, fill, exact)``
+    runs K1 with the call's geometry.
+
+    C == 1, linear, no anti-aliasing: the fused TIO_LABEL_PV mode (no one-hot channels in HBM).
+    C == 1 otherwise: one-hot channels -> [blur] -> K1 with the reference's exact coordinate chain
+    (argmax ties and the 0.5 threshold are decided by the last bit) -> argmax / pad label.
+    C > 1: the channels are sampled as they are, zero padding, floating-point result."""
+    if one_hot_interpolation not in ("nearest", "linear"):
+        raise NotImplementedError(
+            f'one_hot_label_interpolation "{one_hot_interpolation}" is not implemented in torchio_b200'
+            " (orders 0-1 only)")
+    mode = ops.NEAREST if one_hot_interpolation == "nearest" else ops.LINEAR
+    if data.shape[1] > 1:
+        smoothed = data if data.dtype == torch.float32 else data.float()
+        if antialias:
+            smoothed = _antialias(smoothed, a_in, a_out)
+        sampled = resample(smoothed, mode, None, True)
+        return sampled.to(data.dtype) if data.dtype.is_floating_point else sampled
+    native = data if data.dtype in ops.DTYPE_CODES else data.float()
+    if not antialias and mode == ops.LINEAR:
+        pad = torch.full((1,), float(pad_label), dtype=torch.float32, device=data.device)
+        out = resample(native, ops.LABEL_PV, pad, True)
+    else:
+        labels = torch.unique(native)  # ascending: the channel order of the reference
+        one_hot = ops.onehot(native, labels)
+        if antialias:
+            one_hot = _antialias(one_hot, a_in, a_out)
+        sampled = resample(one_hot, mode, None, True)
+        out = ops.label_argmax(sampled, labels, float(pad_label), native.dtype)
+    return out if out.dtype == data.dtype else out.to(data.dtype)
+
+
 def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_interpolation,
                    label_interpolation, antialias, default_pad_value, default_pad_label,
-                   max_displacements=None) -> None:
+                   one_hot_label_interpolation="linear", max_displacements=None) -> None:
     if not names:
         return
     mats, cps, per_instance = geometry
@@ -758,11 +796,23 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
         ib = batch.images[name]
         is_label = issubclass(ib._image_class, LabelMap)
         interp = label_interpolation if is_label else image_interpolation
+        data = ib.data
+        if is_label and interp == LABEL_INTERPOLATION:
+            def run(tensor, mode, fill, exact):
+                return ops.resample(
+                    tensor, mat_d, cp_d, flags_d, a_in.spacing, a_out.spacing, affine_first=affine_first,
+                    mode=mode, fill=fill, out_shape=None if target_space is None else out_shape,
+                    box_hint=box_hint, exact_coords=exact)
+            ib.data = _resample_label_pv(
+                data, run, antialias=antialias, a_in=a_in, a_out=a_out,
+                one_hot_interpolation=one_hot_label_interpolation, pad_label=default_pad_label)
+            keep_original = set(packed.passthrough)
+            ib.affines[:] = [ib.affines[i] if i in keep_original else a_out.clone() for i in range(b)]
+            continue
         if interp not in ("nearest", "linear"):
             raise NotImplementedError(
                 f'interpolation "{interp}" is not implemented in torchio_b200 (orders 0-1 only)'
             )
-        data = ib.data
         native = data if data.dtype in ops.DTYPE_CODES else data.float()
         if info is None:
             fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
