@@ -100,9 +100,10 @@ def spatial(images, params):
     names = params.get("selected_images", [])
     if not names:
         return
-    if params.get("target") is not None or params.get("antialias", False):
-        # resampling onto another grid / the anti-alias pre-filter: the torch restatement
-        # (F.grid_sample, F.pad + F.conv3d — the reference's own calls) is the oracle
+    if (params.get("target") is not None or params.get("antialias", False)
+            or params.get("label_interpolation") == "label"):
+        # resampling onto another grid / the anti-alias pre-filter / partial-volume labels: the
+        # torch restatement (F.grid_sample, F.pad + F.conv3d — the reference's own calls) is the oracle
         return tp.spatial(images, params)
     first = images[names[0]]
     shape = tuple(first["data"].shape[-3:])

@@ -144,11 +144,47 @@ def fill_value_for(data, kind, pad_value, pad_label):
         return float(pad_label)
     if isinstance(pad_value, (int, float)):
         return float(pad_value)
-    if pad_value != "minimum":
+    if pad_value == "minimum":
+        return torch.as_tensor(
+            [float(ch.min().item()) for ch in data[0]], dtype=torch.float32
+        )
+    if pad_value not in ("mean", "otsu"):
         raise NotImplementedError(pad_value)
     return torch.as_tensor(
-        [float(ch.min().item()) for ch in data[0]], dtype=torch.float32
+        [border_mean(ch, pad_value == "otsu") for ch in data[0]], dtype=torch.float32
     )
+
+
+def border_mean(tensor, filter_otsu):
+    """spatial.py:2105-2131: mean of the six boundary faces, optionally only of the voxels
+    below their Otsu threshold."""
+    borders = torch.cat([
+        tensor[0, :, :].ravel(), tensor[-1, :, :].ravel(), tensor[:, 0, :].ravel(),
+        tensor[:, -1, :].ravel(), tensor[:, :, 0].ravel(), tensor[:, :, -1].ravel(),
+    ]).float()
+    if not filter_otsu:
+        return float(borders.mean().item())
+    values = borders[borders < otsu_threshold(borders)]
+    return float(values.mean().item()) if values.numel() > 0 else float(borders.mean().item())
+
+
+def otsu_threshold(values):
+    """spatial.py:2133-2168: sweep over the sorted values maximising the between-class variance
+    (python floats, running sums)."""
+    sorted_values, _ = values.sort()
+    n = sorted_values.numel()
+    if n == 0:
+        return 0.0
+    total = float(sorted_values.sum().item())
+    best_threshold, best_variance, background = float(sorted_values[0].item()), 0.0, 0.0
+    for count, item in enumerate(sorted_values[:-1].tolist(), start=1):
+        background += item
+        mean_b = background / count
+        mean_f = (total - background) / (n - count)
+        variance = (count / n) * ((n - count) / n) * (mean_b - mean_f) ** 2
+        if variance > best_variance:
+            best_variance, best_threshold = variance, item
+    return best_threshold
 
 
 def label_partial_volume(data, vox, in_shape, a_in, a_out, antialias_on, one_hot_mode, pad_label):

@@ -85,6 +85,10 @@ CASES = [
          images={"t1": "scalar", "seg": "int32"},
          transform=("Affine", {**_AFF, "default_pad_value": -1.5,
                                "default_pad_label": 7})),
+    dict(name="affine_fill_mean", seed=24, shape=(16, 14, 12), batch=2, channels=2,
+         images={"t1": "scalar"}, transform=("Affine", {**_AFF, "default_pad_value": "mean"})),
+    dict(name="affine_fill_otsu", seed=25, shape=(16, 14, 12), batch=2, channels=2,
+         images={"t1": "scalar"}, transform=("Affine", {**_AFF, "default_pad_value": "otsu"})),
     dict(name="affine_nearest_image", seed=15, shape=(16, 14, 12), batch=2,
          images={"t1": "scalar"},
          transform=("Affine", {**_AFF, "image_interpolation": "nearest"})),

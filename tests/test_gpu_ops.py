@@ -421,3 +421,54 @@ def test_nearest_tile_path_is_bit_exact_with_general_path(dtype, elastic):
         general = ops.resample(lab, mat, cp, flags, one, one, box_hint=-1, **kw)
         assert torch.equal(tiled, general)
         assert tiled.dtype == dtype
+
+
+def test_stream_yields_what_the_plain_calls_return():
+    """`for out in pipeline.stream(batches)` keeps a batch in flight (copy-in of batch n+1 under
+    the copy-out of batch n); every yielded batch, its history and the RNG consumption must
+    equal calling the pipeline batch by batch."""
+    import json
+    import warnings
+
+    import torchio_b200 as tio
+
+    def make():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pipe = tio.Compose([
+                tio.Affine(scales=(0.9, 1.1), degrees=(-10, 10), p=0.8), tio.ElasticDeformation(),
+                tio.BiasField(), tio.Blur(std=(0, 2)), tio.Noise(std=(0, 0.25)),
+                tio.Gamma(log_gamma=(-0.3, 0.3))], copy=False)
+        pipe.chunk_size = 2
+        return pipe
+
+    def batches():
+        for t in range(4):
+            g = torch.Generator().manual_seed(50 + t)
+            x = (torch.rand((5, 1, 24, 28, 32), generator=g) + 0.1).pin_memory()
+            lab = (torch.rand((5, 1, 24, 28, 32), generator=g) * 4).to(torch.int16).pin_memory()
+            yield tio.SubjectsBatch({
+                "t1": tio.ImagesBatch(x, [tio.AffineMatrix() for _ in range(5)]),
+                "seg": tio.ImagesBatch(lab, [tio.AffineMatrix() for _ in range(5)], image_class=tio.LabelMap)})
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(91)
+        pipe = make()
+        plain = [pipe(b) for b in batches()]
+        after_plain = torch.rand(1).item()
+        for depth in (0, 1, 3):
+            torch.manual_seed(91)
+            streamed = list(make().stream(batches(), depth=depth))
+            assert torch.rand(1).item() == after_plain
+            assert len(streamed) == len(plain)
+            for a, b in zip(plain, streamed):
+                assert b.images["t1"].data.device.type == "cpu"
+                assert torch.equal(a.images["t1"].data, b.images["t1"].data)
+                assert torch.equal(a.images["seg"].data, b.images["seg"].data)
+                ha = [(t.name, json.dumps(t.params, sort_keys=True)) for t in a.applied_transforms]
+                hb = [(t.name, json.dumps(t.params, sort_keys=True)) for t in b.applied_transforms]
+                assert ha == hb
+    ticket = make().submit(next(batches()))
+    out = ticket.result()
+    assert ticket.done() and out.images["t1"].data.device.type == "cpu"

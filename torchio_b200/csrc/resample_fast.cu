@@ -102,15 +102,44 @@ __device__ __noinline__ void slow_tile(const ResampleArgs& a, const TileArgs& ta
   exact_planes<HAS_CP, HAS_FILL>(a, ta, b, HAS_CP && (rec.w & 1024), i0, i1, oj, ok);
 }
 
+// Taps of the upper plane (i + 1) of the previous voxel of the walk and the shared-memory address
+// they were read from.  Along the walk the sampling point advances by about one voxel in I and
+// by little in J/K, so for most voxels the lower-plane taps ARE the previous voxel's upper-plane
+// taps: they stay in registers and the four lower-plane loads run predicated, only for the lanes
+// whose cell moved in J/K or skipped a plane.  ncu (profiles/r2_ncu_full_k1_fast_batch32.csv): the
+// kernel sits at 82 % of the shared-memory data pipe with 2.1 wavefronts per LDS (rotated rows
+// step across box rows); a predicated load touches ~20 % of the lanes and takes ~1.3.
+struct Carry {
+  float u00, u01, u10, u11;
+  uint32_t up;  // address of the (i + 1, j, k) tap the values came from; 0xffffffff = none
+};
+
+template <int C2>
+__device__ __forceinline__ void lds4_unless(float& v00, float& v01, float& v10, float& v11, const uint32_t addr,
+                                            const uint32_t same) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.u32 p, %4, %5;\n\t"
+      "@p ld.shared.f32 %0, [%4];\n\t"
+      "@p ld.shared.f32 %1, [%4+4];\n\t"
+      "@p ld.shared.f32 %2, [%4+%6];\n\t"
+      "@p ld.shared.f32 %3, [%4+%7];\n\t"
+      "}"
+      : "+f"(v00), "+f"(v01), "+f"(v10), "+f"(v11)
+      : "r"(addr), "r"(same), "n"(4 * C2), "n"(4 * C2 + 4));
+}
+
 // One pair of planes (rel, rel + 1) of a column.  MASKED (border tile with a fill value): the
 // reference's mask, the trilinear weight sum of the in-bounds corners, is separable — per axis
 // the in-bounds weight is the trapezoid sat(min(u - (lo - 1), (hi + 1) - u)) — so it is
 // evaluated from the same coordinates; voxels whose mask is within 1e-3 of the 0.5 threshold
 // (coordinate noise moves it by < 1e-4) are flagged and recomputed exactly afterwards.
-template <int C1, int C2, bool MASKED>
+template <int C1, int C2, bool MASKED, bool REUSE>
 __device__ __forceinline__ void pair_step(const f2 rel2, const f2 A0, const f2 A1, const f2 A2, const f2 B0,
                                           const f2 B1, const f2 B2, const uint32_t kb, const float* tz,
-                                          const float fill_c, float& va, float& vb, bool& unc_a, bool& unc_b) {
+                                          const float fill_c, float& va, float& vb, bool& unc_a, bool& unc_b,
+                                          Carry& carry) {
   const f2 magic2 = bc(kMagic), mmagic2 = bc(-kMagic);
   const f2 u0 = fma2(rel2, B0, A0), u1 = fma2(rel2, B1, A1), u2 = fma2(rel2, B2, A2);
   const f2 s0 = add2_rd(u0, magic2), s1 = add2_rd(u1, magic2), s2 = add2_rd(u2, magic2);
@@ -122,14 +151,30 @@ __device__ __forceinline__ void pair_step(const f2 rel2, const f2 A0, const f2 A
   unpack2(idx, ia, ib);
   const uint32_t addr_a = ((uint32_t)__float_as_int(ia) << 2) + kb;
   const uint32_t addr_b = ((uint32_t)__float_as_int(ib) << 2) + kb;
-  const f2 v000 = pack2(lds_f32<0>(addr_a), lds_f32<0>(addr_b));
-  const f2 v001 = pack2(lds_f32<4>(addr_a), lds_f32<4>(addr_b));
-  const f2 v010 = pack2(lds_f32<4 * C2>(addr_a), lds_f32<4 * C2>(addr_b));
-  const f2 v011 = pack2(lds_f32<4 * C2 + 4>(addr_a), lds_f32<4 * C2 + 4>(addr_b));
-  const f2 v100 = pack2(lds_f32<4 * C1>(addr_a), lds_f32<4 * C1>(addr_b));
-  const f2 v101 = pack2(lds_f32<4 * C1 + 4>(addr_a), lds_f32<4 * C1 + 4>(addr_b));
-  const f2 v110 = pack2(lds_f32<4 * (C1 + C2)>(addr_a), lds_f32<4 * (C1 + C2)>(addr_b));
-  const f2 v111 = pack2(lds_f32<4 * (C1 + C2) + 4>(addr_a), lds_f32<4 * (C1 + C2) + 4>(addr_b));
+  f2 v000, v001, v010, v011, v100, v101, v110, v111;
+  if (REUSE) {
+    const float ua00 = lds_f32<4 * C1>(addr_a), ua01 = lds_f32<4 * C1 + 4>(addr_a);
+    const float ua10 = lds_f32<4 * (C1 + C2)>(addr_a), ua11 = lds_f32<4 * (C1 + C2) + 4>(addr_a);
+    const float ub00 = lds_f32<4 * C1>(addr_b), ub01 = lds_f32<4 * C1 + 4>(addr_b);
+    const float ub10 = lds_f32<4 * (C1 + C2)>(addr_b), ub11 = lds_f32<4 * (C1 + C2) + 4>(addr_b);
+    float la00 = carry.u00, la01 = carry.u01, la10 = carry.u10, la11 = carry.u11;
+    lds4_unless<C2>(la00, la01, la10, la11, addr_a, carry.up);
+    float lb00 = ua00, lb01 = ua01, lb10 = ua10, lb11 = ua11;
+    lds4_unless<C2>(lb00, lb01, lb10, lb11, addr_b, addr_a + 4u * C1);
+    carry.u00 = ub00; carry.u01 = ub01; carry.u10 = ub10; carry.u11 = ub11;
+    carry.up = addr_b + 4u * C1;
+    v000 = pack2(la00, lb00); v001 = pack2(la01, lb01); v010 = pack2(la10, lb10); v011 = pack2(la11, lb11);
+    v100 = pack2(ua00, ub00); v101 = pack2(ua01, ub01); v110 = pack2(ua10, ub10); v111 = pack2(ua11, ub11);
+  } else {
+    v000 = pack2(lds_f32<0>(addr_a), lds_f32<0>(addr_b));
+    v001 = pack2(lds_f32<4>(addr_a), lds_f32<4>(addr_b));
+    v010 = pack2(lds_f32<4 * C2>(addr_a), lds_f32<4 * C2>(addr_b));
+    v011 = pack2(lds_f32<4 * C2 + 4>(addr_a), lds_f32<4 * C2 + 4>(addr_b));
+    v100 = pack2(lds_f32<4 * C1>(addr_a), lds_f32<4 * C1>(addr_b));
+    v101 = pack2(lds_f32<4 * C1 + 4>(addr_a), lds_f32<4 * C1 + 4>(addr_b));
+    v110 = pack2(lds_f32<4 * (C1 + C2)>(addr_a), lds_f32<4 * (C1 + C2)>(addr_b));
+    v111 = pack2(lds_f32<4 * (C1 + C2) + 4>(addr_a), lds_f32<4 * (C1 + C2) + 4>(addr_b));
+  }
   const f2 a00 = fma2(hi2, sub2(v001, v000), v000);
   const f2 a01 = fma2(hi2, sub2(v011, v010), v010);
   const f2 a10 = fma2(hi2, sub2(v101, v100), v100);
@@ -155,7 +200,7 @@ __device__ __forceinline__ void pair_step(const f2 rel2, const f2 A0, const f2 A
   }
 }
 
-template <int BOX, bool HAS_CP, bool HAS_FILL, int LK>
+template <int BOX, bool HAS_CP, bool HAS_FILL, bool REUSE>
 __global__ void __launch_bounds__(256, BOX <= 22 ? 4 : 3)
 resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_s,
                      const __grid_constant__ ResampleArgs a, const __grid_constant__ TileArgs ta,
@@ -215,7 +260,7 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     if (lane == 0) *chg_mask = mask;
   }
   int jrow, kcol;
-  lane_column<BOX, LK>(tid, jrow, kcol);
+  lane_column<BOX, 16>(tid, jrow, kcol);
   // an axis of size 1 collapses to u = 0 whatever the matrix says ((size - 1) == 0 in the
   // reference's un-normalise step)
   const float keep[3] = {a.I > 1 ? 1.0f : 0.0f, a.J > 1 ? 1.0f : 0.0f, a.K > 1 ? 1.0f : 0.0f};
@@ -325,6 +370,9 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     char* out_b = out_a + ostride * (long long)sizeof(float);
     const float fill_c = masked ? a.fill[c] : 0.0f;
     f2 rel2 = pack2(0.0f, 1.0f);
+    Carry carry;
+    carry.u00 = carry.u01 = carry.u10 = carry.u11 = 0.0f;
+    carry.up = 0xffffffffu;  // the box was (re)loaded: nothing to reuse
     // pairs [p, p + count) with the column constants as they are; MASKED resolved outside
     auto run = [&](const int p0, const int count, auto masked_tag, auto small_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
@@ -333,8 +381,8 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       for (int q = 0; q < count; ++q) {
         float va, vb;
         bool unc_a = false, unc_b = false;
-        pair_step<SMALL ? C1S : C1, SMALL ? C2S : C2, MASKED>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb,
-                                                                unc_a, unc_b);
+        pair_step<SMALL ? C1S : C1, SMALL ? C2S : C2, MASKED, REUSE>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c,
+                                                                       va, vb, unc_a, unc_b, carry);
         *reinterpret_cast<float*>(out_a) = va;
         *reinterpret_cast<float*>(out_b) = vb;
         if (MASKED) {
@@ -379,8 +427,10 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
       for (int p = 0; p < XT / 2; ++p) {
         float va, vb;
         bool unc_a = false, unc_b = false;
-        if (masked) pair_step<C1, C2, true>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
-        else pair_step<C1, C2, false>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b);
+        if (masked)
+          pair_step<C1, C2, true, REUSE>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b, carry);
+        else
+          pair_step<C1, C2, false, REUSE>(rel2, A0, A1, A2, B0, B1, B2, kb, tz, fill_c, va, vb, unc_a, unc_b, carry);
         *reinterpret_cast<float*>(out_a) = va;
         *reinterpret_cast<float*>(out_b) = vb;
         if (HAS_FILL) {
@@ -397,48 +447,47 @@ resample_fast_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   if (HAS_FILL && unsafe) exact_fix<HAS_CP, HAS_FILL>(a, ta, b, elastic, i0, unsafe, j0 + jrow, k0 + kcol);
 }
 
-template <int BOX, bool HAS_CP, int LK>
-static void launch_fast_lk(const CUtensorMap& tm, const CUtensorMap& tms, const ResampleArgs& a, const TileArgs& ta,
-                           dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
+template <int BOX, bool HAS_CP, bool REUSE>
+static void launch_fast_r(const CUtensorMap& tm, const CUtensorMap& tms, const ResampleArgs& a, const TileArgs& ta,
+                          dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
   if (a.fill) {
-    cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, true, LK>,
+    cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, true, REUSE>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_fast_kernel<BOX, HAS_CP, true, LK><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
+    resample_fast_kernel<BOX, HAS_CP, true, REUSE><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
   } else {
-    cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, false, LK>,
+    cudaFuncSetAttribute(resample_fast_kernel<BOX, HAS_CP, false, REUSE>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resample_fast_kernel<BOX, HAS_CP, false, LK><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
+    resample_fast_kernel<BOX, HAS_CP, false, REUSE><<<grid, 256, smem, st>>>(tm, tms, a, ta, records);
   }
 }
 
 template <int BOX>
 static void launch_fast(const CUtensorMap& tm, const CUtensorMap& tms, const ResampleArgs& a, const TileArgs& ta,
-                        dim3 grid, size_t smem, int lk, const int4* records, cudaStream_t st) {
+                        dim3 grid, size_t smem, int reuse, const int4* records, cudaStream_t st) {
+  // bit 0: affine-only launches, bit 1: launches with a control grid
   if (a.cp) {
-    if (lk == 4) launch_fast_lk<BOX, true, 4>(tm, tms, a, ta, grid, smem, records, st);
-    else if (lk == 8) launch_fast_lk<BOX, true, 8>(tm, tms, a, ta, grid, smem, records, st);
-    else launch_fast_lk<BOX, true, 16>(tm, tms, a, ta, grid, smem, records, st);
+    if (reuse & 2) launch_fast_r<BOX, true, true>(tm, tms, a, ta, grid, smem, records, st);
+    else launch_fast_r<BOX, true, false>(tm, tms, a, ta, grid, smem, records, st);
   } else {
-    if (lk == 4) launch_fast_lk<BOX, false, 4>(tm, tms, a, ta, grid, smem, records, st);
-    else if (lk == 8) launch_fast_lk<BOX, false, 8>(tm, tms, a, ta, grid, smem, records, st);
-    else launch_fast_lk<BOX, false, 16>(tm, tms, a, ta, grid, smem, records, st);
+    if (reuse & 1) launch_fast_r<BOX, false, true>(tm, tms, a, ta, grid, smem, records, st);
+    else launch_fast_r<BOX, false, false>(tm, tms, a, ta, grid, smem, records, st);
   }
 }
 
 // fp32 + trilinear tiles of the launch prepared by launch_resample_tile (tensor map, tile
-// arguments, bounds records); TIO_B200_K1_LK = 16 | 8 | 4 picks the lane layout (development knob)
+// arguments, bounds records).  TIO_B200_K1_REUSE (development knob, default 3): bit 0 / bit 1 =
+// keep the upper-plane taps in registers along the walk for affine / elastic launches.
 void launch_resample_fast(int box, const CUtensorMap& tm, const CUtensorMap& tm_small, const ResampleArgs& a,
                           const TileArgs& ta, dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
-  static const int lk = []() {
-    const char* e = getenv("TIO_B200_K1_LK");
-    const int v = e ? atoi(e) : 16;
-    return (v == 4 || v == 8) ? v : 16;
+  static const int reuse = []() {
+    const char* e = getenv("TIO_B200_K1_REUSE");
+    return e ? atoi(e) & 3 : 3;
   }();
-  if (box == 20) launch_fast<20>(tm, tm_small, a, ta, grid, smem, lk, records, st);
-  else if (box == 22) launch_fast<22>(tm, tm_small, a, ta, grid, smem, lk, records, st);
-  else if (box == 24) launch_fast<24>(tm, tm_small, a, ta, grid, smem, lk, records, st);
-  else if (box == 28) launch_fast<28>(tm, tm_small, a, ta, grid, smem, lk, records, st);
-  else launch_fast<32>(tm, tm_small, a, ta, grid, smem, lk, records, st);
+  if (box == 20) launch_fast<20>(tm, tm_small, a, ta, grid, smem, reuse, records, st);
+  else if (box == 22) launch_fast<22>(tm, tm_small, a, ta, grid, smem, reuse, records, st);
+  else if (box == 24) launch_fast<24>(tm, tm_small, a, ta, grid, smem, reuse, records, st);
+  else if (box == 28) launch_fast<28>(tm, tm_small, a, ta, grid, smem, reuse, records, st);
+  else launch_fast<32>(tm, tm_small, a, ta, grid, smem, reuse, records, st);
 }
 
 }  // namespace tio

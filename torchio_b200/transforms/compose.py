@@ -24,6 +24,22 @@ from . import intensity as _int
 _stream_local = _threading.local()
 
 
+class Pending:
+    """Ticket of `Compose.submit`: the transformed batch once the device has delivered it."""
+
+    def __init__(self, batch, unwrap, event) -> None:
+        self._batch, self._unwrap, self._event = batch, unwrap, event
+
+    def done(self) -> bool:
+        return self._event is None or self._event.query()
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return _finish(self._batch, self._unwrap)
+
+
 class Compose(Transform):
     def __init__(self, transforms: Sequence[Transform] | Mapping[str, Transform] | None = None,
                  *, copy: bool = True, **kwargs: Any) -> None:
@@ -36,16 +52,42 @@ class Compose(Transform):
             self.transforms = list(transforms)
 
     def forward(self, data: Any) -> Any:
+        return self.submit(data).result()
+
+    def submit(self, data: Any) -> "Pending":
+        """Issue the whole pipeline for ``data`` and return without waiting for the device.
+
+        For a host-resident batch that is streamed through the device in slices, every copy
+        and kernel is queued and the call returns while they run; `Pending.result()` waits
+        for the last copy-out and hands back what `forward` returns.  Anything else is
+        executed as `forward` does and the ticket is already complete.  Submitting batch
+        n+1 before collecting batch n lets its copy-in overlap the copy-out of batch n
+        (PCIe is full duplex) — `stream` does exactly that."""
         if self.copy:
             data = _copy.deepcopy(data)
         batch, unwrap = wrap_input(data)
         chunk = self._chunk_size(batch)
         if chunk:
-            batch = self._forward_streamed(batch, chunk)
-        else:
-            with _Staging(batch):
-                batch = self._forward_batch(batch)
-        return _finish(batch, unwrap)
+            batch, done = self._forward_streamed(batch, chunk)
+            return Pending(batch, unwrap, done)
+        with _Staging(batch):
+            batch = self._forward_batch(batch)
+        return Pending(batch, unwrap, None)
+
+    def stream(self, batches, depth: int = 1):
+        """Loader-style application: ``for out in pipeline.stream(loader)`` yields
+        ``pipeline(batch)`` for every batch of ``loader``, in order, with up to ``depth``
+        later batches already issued to the device while the caller consumes the current one.
+        Results and RNG consumption equal calling the pipeline batch by batch."""
+        if depth < 0:
+            raise ValueError(f"depth must be >= 0, got {depth}")
+        window: list[Pending] = []
+        for data in batches:
+            window.append(self.submit(data))
+            if len(window) > depth:
+                yield window.pop(0).result()
+        while window:
+            yield window.pop(0).result()
 
     #: Elements per slice when a host-resident batch is streamed through the device
     #: (None = choose from the batch's size; 0 = never stream).
@@ -144,7 +186,7 @@ class Compose(Transform):
                     outputs[name][b0:b1].copy_(result, non_blocking=True)
                     affines[name].extend(sub.images[name].affines)
             del staged, sub
-        d2h.synchronize()
+        done = d2h.record_event()
         caller.wait_stream(compute)
         for name in names:
             ib = batch.images[name]
@@ -153,7 +195,7 @@ class Compose(Transform):
         for _, applied in plan:
             for transform, params in applied:
                 transform._record(batch, params)
-        return batch
+        return batch, done
 
     def _streams(self, device):
         """(copy-in, kernels, copy-out) streams of the calling thread for ``device``.  Kept per

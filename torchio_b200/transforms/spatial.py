@@ -8,11 +8,11 @@ three small tables and runs ONE fused CUDA pass per image
 (`ops.resample`, K1) instead of materialising a sampling grid and calling
 ``grid_sample`` twice (spatial.py:1110-1272, 1504-1857).
 
-Supported natively: interpolation orders 0-1 (``"nearest"``/``"linear"``),
-``target=None`` or a concrete ``(shape, affine)`` space, fills ``"minimum"``,
-``"mean"`` or numeric.  Out of scope this round (raise NotImplementedError):
-B-spline orders >= 2, ``label_interpolation="label"``, ``antialias``,
-``default_pad_value="otsu"``, random/path/str targets.
+Supported natively: interpolation orders 0-1 (``"nearest"``/``"linear"``) and the partial-volume
+``label_interpolation="label"``; ``target=None``, a concrete ``(shape, affine)`` space, an
+image, an image name or (random) spacings; ``antialias``; fills ``"minimum"``, ``"mean"``,
+``"otsu"`` or numeric.  Raise NotImplementedError: B-spline orders >= 2 (the reference delegates
+them to ``torch-interpol``, which is neither vendored nor installed) and file-path targets.
 """
 
 from __future__ import annotations
@@ -714,6 +714,42 @@ class _SpatialInverse(SpatialTransform):
         return batch
 
 
+def _border_faces(data: Tensor) -> Tensor:
+    """(C, n) values of the six boundary faces of sample 0, in the reference's order (edges and
+    corners counted once per face they belong to, spatial.py:2115-2124)."""
+    x = data[0]
+    c = x.shape[0]
+    faces = [x[:, 0], x[:, -1], x[:, :, 0], x[:, :, -1], x[:, :, :, 0], x[:, :, :, -1]]
+    return torch.cat([f.reshape(c, -1) for f in faces], dim=1)
+
+
+def _otsu_border_mean(borders: np.ndarray) -> float:
+    """`_border_mean(filter_otsu=True)` of one channel (spatial.py:2105-2168).  The reference sweeps
+    the sorted values in a Python loop with float64 running sums; cumsum is the same left-to-right
+    accumulation, so threshold and mean are the reference's bit for bit (fp32 mean included)."""
+    values = np.sort(borders.astype(np.float32), kind="stable")
+    n = values.size
+    if n == 0:
+        return 0.0
+    as64 = values.astype(np.float64)
+    total = float(torch.from_numpy(values).sum().item())  # sorted_values.sum(): torch's fp32 reduction
+    threshold = float(values[0])
+    if n > 1:
+        counts = np.arange(1, n, dtype=np.float64)
+        background = np.cumsum(as64[:-1])
+        mean_b = background / counts
+        mean_f = (total - background) / (n - counts)
+        variance = (counts / n) * ((n - counts) / n) * (mean_b - mean_f) ** 2
+        best = int(np.argmax(variance))  # first maximum, like the strict `>` of the sweep
+        if variance[best] > 0.0:
+            threshold = float(values[best])
+    below = torch.from_numpy(borders.astype(np.float32))
+    below = below[below < threshold]
+    if below.numel() > 0:
+        return float(below.mean().item())
+    return float(torch.from_numpy(borders.astype(np.float32)).mean().item())
+
+
 def _fill_tensor(data: Tensor, is_label: bool, pad_value, pad_label):
     """Device (C,) fill or None (= skip the mask step, only for a python-float
     0.0; spatial.py:2034-2086)."""
@@ -726,11 +762,10 @@ def _fill_tensor(data: Tensor, is_label: bool, pad_value, pad_label):
         first = data[:1]
         return ops.min_sample0(first if first.dtype == torch.float32 else first.float())
     elif pad_value == "mean":  # mean of the six border faces of sample 0
-        x = data[0]
-        faces = [x[:, 0], x[:, -1], x[:, :, 0], x[:, :, -1], x[:, :, :, 0], x[:, :, :, -1]]
-        return torch.cat([f.reshape(c, -1) for f in faces], dim=1).float().mean(dim=1)
-    else:
-        raise NotImplementedError('default_pad_value="otsu" is not implemented in torchio_b200')
+        return _border_faces(data).float().mean(dim=1)
+    else:  # "otsu": mean of the border voxels below their Otsu threshold (spatial.py:2105-2168)
+        borders = _border_faces(data).float().cpu().numpy()  # C x 6 faces: ~1.5 MB at 256^3
+        return torch.tensor([_otsu_border_mean(row) for row in borders], dtype=torch.float32, device=data.device)
     if value == 0.0:
         return None
     return torch.full((c,), value, dtype=torch.float32, device=data.device)
@@ -784,9 +819,20 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
         a_in.numpy(), a_out.numpy(), per_instance=per_instance,
         has_target=target_space is not None,
     )
+    info = chunk_info()
+    if info is not None and info.b0 == 0:
+        # "minimum"/"mean" read batch element 0, which only the first slice of a streamed batch
+        # holds: derive the fills now, even if every element of this slice is gated out
+        for name in names:
+            ib = batch.images[name]
+            is_label = issubclass(ib._image_class, LabelMap)
+            if is_label and label_interpolation == LABEL_INTERPOLATION:
+                continue
+            native = ib.data if ib.data.dtype in ops.DTYPE_CODES else ib.data.float()
+            info.cache[("fill", info.step, name)] = _fill_tensor(native, is_label, default_pad_value,
+                                                                 default_pad_label)
     if packed is None:  # exact no-op: data and affines untouched (spatial.py:579-590)
         return
-    info = chunk_info()
     if info is None:  # streamed batches: checked once on the whole batch (Spatial.plan_checks)
         _folding_warning(cps, max_displacements, out_shape, a_out)
     device = first.data.device
@@ -816,10 +862,7 @@ def _apply_spatial(batch, names, target_space, geometry, *, affine_first, image_
         native = data if data.dtype in ops.DTYPE_CODES else data.float()
         if info is None:
             fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
-        elif info.b0 == 0:  # "minimum"/"mean" read batch element 0: the first slice has it
-            fill = _fill_tensor(native, is_label, default_pad_value, default_pad_label)
-            info.cache[("fill", info.step, name)] = fill
-        else:
+        else:  # streamed: derived from batch element 0 when the first slice came through
             fill = info.cache[("fill", info.step, name)]
         if antialias and not is_label:  # after the fill value (spatial.py:1249-1257): blur what is downsampled
             native = _antialias(native, a_in, a_out)
