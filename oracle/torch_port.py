@@ -606,12 +606,44 @@ def crop(images: dict, params: dict) -> None:
         _shift_origin(img, (i0, j0, k0))
 
 
+def _quantile(values, q):
+    """compute_quantile (transforms/_statistics.py:11-45): kthvalue twice + lerp."""
+    import math
+
+    index = q * (values.numel() - 1)
+    lower = math.floor(index)
+    lower_value = torch.kthvalue(values, lower + 1).values
+    if index == lower:
+        return lower_value
+    upper_value = torch.kthvalue(values, lower + 2).values
+    return lower_value.lerp(upper_value, index - lower)
+
+
 def pad(images: dict, params: dict) -> None:
-    """Pad.apply_transform, non-statistic modes (spatial/pad.py:88-110, _padding.py:83-90)."""
+    """Pad.apply_transform (spatial/pad.py:88-110, _padding.py:41-110): F.pad's modes, or a
+    constant pad with one whole-volume statistic per batch element."""
     i0, i1, j0, j1, k0, k1 = params["padding"]
+    mode = params["padding_mode"]
+    pad_arg = (k0, k1, j0, j1, i0, i1)
     for img in images.values():
-        img["data"] = torch.nn.functional.pad(img["data"], (k0, k1, j0, j1, i0, i1),
-                                              mode=params["padding_mode"], value=params["fill"])
+        data = img["data"]
+        if mode not in ("mean", "median", "minimum"):
+            img["data"] = torch.nn.functional.pad(data, pad_arg, mode=mode, value=params["fill"])
+        else:
+            flat = data.flatten(start_dim=1)
+            if mode == "minimum":
+                statistic = flat.amin(dim=1)
+            else:
+                float_flat = flat if data.dtype in (torch.float32, torch.float64) else flat.float()
+                if mode == "mean":
+                    statistic = float_flat.mean(dim=1)
+                else:
+                    statistic = torch.stack([_quantile(values, 0.5) for values in float_flat])
+                statistic = statistic.to(data.dtype)
+            padded = torch.nn.functional.pad(data, pad_arg)
+            interior = torch.nn.functional.pad(
+                torch.ones((1, 1, *data.shape[-3:]), dtype=torch.bool), pad_arg)
+            img["data"] = torch.where(interior, padded, statistic.reshape(-1, 1, 1, 1, 1))
         _shift_origin(img, (-i0, -j0, -k0))
 
 

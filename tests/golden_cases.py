@@ -210,6 +210,14 @@ NEIGHBOUR_CASES = [
          transform=("Pad", {"padding": 4, "padding_mode": "replicate"})),
     dict(name="pad_circular", seed=88, shape=(8, 9, 10), batch=2, images={"t1": "scalar"},
          transform=("Pad", {"padding": (2, 3, 4, 5, 6, 7), "padding_mode": "circular"})),
+    # whole-volume statistic per element (_padding.py:41-110)
+    dict(name="pad_minimum", seed=90, shape=(8, 9, 10), batch=3, channels=2, shift=0.3,
+         images={"t1": "scalar", "seg": "int16"},
+         transform=("Pad", {"padding": (2, 1, 0, 3, 1, 2), "padding_mode": "minimum"})),
+    dict(name="pad_median", seed=91, shape=(9, 8, 11), batch=2, channels=2, shift=0.3,
+         images={"t1": "scalar"}, transform=("Pad", {"padding": (1, 2, 3), "padding_mode": "median"})),
+    dict(name="pad_mean", seed=92, shape=(8, 9, 10), batch=2, shift=0.3,
+         images={"t1": "scalar"}, transform=("Pad", {"padding": 2, "padding_mode": "mean"})),
     dict(name="compose_flip_pad_affine_crop", seed=89, shape=(16, 16, 16), batch=2,
          images={"t1": "scalar", "seg": "int16"},
          transform=[("Flip", {"axes": (0, 1, 2), "flip_probability": 0.5}),

@@ -309,7 +309,8 @@ def crop_patches(volume: Tensor, corners, size, out: Tensor | None = None) -> Te
 PAD_MODES = {"constant": 0, "replicate": 1, "reflect": 2, "circular": 3}
 
 
-def remap(src: Tensor, out_shape, offsets, *, mode: str = "constant", fill=0, flip: Tensor | None = None) -> Tensor:
+def remap(src: Tensor, out_shape, offsets, *, mode: str = "constant", fill=0, flip: Tensor | None = None,
+          out: Tensor | None = None) -> Tensor:
     """Flip / Crop / Pad in one pass: ``out[..., o] = src[..., o - offset]`` per spatial
     axis with F.pad's out-of-range rules, then per-element axis reversal (``flip``: (B,)
     uint8 cuda, bit 0 I, 1 J, 2 K).  flip.py:233-263, crop.py:84-101, _padding.py:73-104."""
@@ -319,7 +320,13 @@ def remap(src: Tensor, out_shape, offsets, *, mode: str = "constant", fill=0, fl
     src = src.contiguous()
     b, c, i, j, k = (int(v) for v in src.shape)
     oi, oj, ok = (int(v) for v in out_shape)
-    dst = torch.empty((b, c, oi, oj, ok), dtype=src.dtype, device=src.device)
+    if out is None:
+        dst = torch.empty((b, c, oi, oj, ok), dtype=src.dtype, device=src.device)
+    else:
+        dst = out
+        if (tuple(dst.shape) != (b, c, oi, oj, ok) or dst.dtype != src.dtype or dst.device != src.device
+                or not dst.is_contiguous()):
+            raise ValueError("remap: `out` must be a contiguous (B, C, *out_shape) block of the source's dtype/device")
     fill_host = torch.tensor([fill]).to(src.dtype)  # F.pad casts the value to the tensor's dtype
     with torch.cuda.device(src.device):
         _native.call(

@@ -11,6 +11,7 @@ origin, flip leaves the affine untouched).
 
 from __future__ import annotations
 
+import warnings
 from collections.abc import Sequence
 from typing import Any
 
@@ -197,6 +198,52 @@ class Crop(SpatialTransform):
 _PADDING_MODES = ("constant", "reflect", "replicate", "circular", "mean", "median", "minimum")
 
 
+def _padding_statistics(data, mode: str) -> list:
+    """One whole-volume statistic per batch element (`_compute_padding_statistic`,
+    _padding.py:41-68), computed where the batch lives: minimum = `tio_min_sample0` over the
+    element, mean = `tio_moments` (fp64 sums; the reference's fp32 `mean()` agrees to rounding),
+    median = the exact radix select behind `compute_quantile(values, 0.5)`."""
+    from .intensity import _lerp_f32
+
+    b = data.shape[0]
+    if mode == "minimum":
+        if data.dtype == torch.float32:
+            mins = [ops.min_sample0(data[i:i + 1].reshape(1, 1, -1, 1, 1)) for i in range(b)]
+            return torch.cat(mins).tolist()
+        return data.flatten(start_dim=1).amin(dim=1).tolist()
+    if not torch.is_floating_point(data):
+        warnings.warn(
+            f'The constant value computed for padding mode "{mode}"'
+            " might be truncated in the output, as the data type of the input"
+            " image is not float. Consider converting the image to a floating"
+            " point type before applying this transform.",
+            RuntimeWarning, stacklevel=4)
+    flat = data if data.dtype == torch.float32 else data.float()
+    values = []
+    for i in range(b):
+        element = flat[i].reshape(-1)
+        if mode == "mean":
+            total, _, count = ops.moments(element)
+            values.append(float(np.float32(total / count)))
+        else:
+            neighbours, weights, _ = ops.quantile_neighbours(element, [0.5])
+            values.append(neighbours[0] if weights[0] == 0
+                          else _lerp_f32(neighbours[0], neighbours[1], weights[0]))
+    return values
+
+
+def _remap_padded(data, out_shape, offsets, mode: str, fill):
+    """`ops.remap` with F.pad's modes, or a constant pad per element with its own whole-volume
+    statistic (`pad_tensor`, _padding.py:71-110)."""
+    if mode in ops.PAD_MODES:
+        return ops.remap(data, out_shape, offsets, mode=mode, fill=fill)
+    statistics = _padding_statistics(data, mode)
+    out = torch.empty((*data.shape[:2], *out_shape), dtype=data.dtype, device=data.device)
+    for i, value in enumerate(statistics):
+        ops.remap(data[i:i + 1], out_shape, offsets, mode="constant", fill=value, out=out[i:i + 1])
+    return out
+
+
 class Pad(SpatialTransform):
     """Add a border of voxels to each side of the volume (pad.py:37-122)."""
 
@@ -214,14 +261,10 @@ class Pad(SpatialTransform):
     def apply_transform(self, batch: SubjectsBatch, params: dict[str, Any]) -> SubjectsBatch:
         i0, i1, j0, j1, k0, k1 = params["padding"]
         mode = params["padding_mode"]
-        if mode not in ops.PAD_MODES:
-            raise NotImplementedError(
-                f'padding_mode "{mode}" (whole-volume statistic) is not implemented in torchio_b200'
-            )
         for ib in self._get_images(batch).values():
             si, sj, sk = ib.data.shape[-3:]
-            ib.data = ops.remap(ib.data, (si + i0 + i1, sj + j0 + j1, sk + k0 + k1), (i0, j0, k0),
-                                mode=mode, fill=params["fill"])
+            ib.data = _remap_padded(ib.data, (si + i0 + i1, sj + j0 + j1, sk + k0 + k1), (i0, j0, k0),
+                                    mode, params["fill"])
             _shift_origins(ib, (-i0, -j0, -k0))
         return batch
 
@@ -318,17 +361,13 @@ class CropOrPad(SpatialTransform):
         padding, cropping = params["padding"], params["cropping"]
         if padding is None and cropping is None:
             return batch
-        if padding is not None and self.padding_mode not in ops.PAD_MODES:
-            raise NotImplementedError(
-                f'padding_mode "{self.padding_mode}" (whole-volume statistic) is not implemented in torchio_b200'
-            )
         p = padding or (0,) * 6
         c = cropping or (0,) * 6
         for ib in self._get_images(batch).values():
             si, sj, sk = ib.data.shape[-3:]
             out = (si + p[0] + p[1] - c[0] - c[1], sj + p[2] + p[3] - c[2] - c[3], sk + p[4] + p[5] - c[4] - c[5])
-            ib.data = ops.remap(ib.data, out, (p[0] - c[0], p[2] - c[2], p[4] - c[4]),
-                                mode=self.padding_mode if padding is not None else "constant", fill=self.fill)
+            ib.data = _remap_padded(ib.data, out, (p[0] - c[0], p[2] - c[2], p[4] - c[4]),
+                                    self.padding_mode if padding is not None else "constant", self.fill)
             _shift_origins(ib, (c[0] - p[0], c[2] - p[2], c[4] - p[4]))
         # the records Compose([Pad, Crop]) leaves behind (crop_or_pad.py:609-633)
         from .base import AppliedTransform
