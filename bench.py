@@ -250,30 +250,45 @@ def run_b200(args, rank, world, local_rank):
             for _ in range(n):
                 yield make_batch(host)
 
-        def run_stream(n):
+        def run_stream(n, step_ms=None):
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                last = None
+                last, t_prev = None, time.perf_counter()
                 for last in pipeline.stream(host_batches(n), depth=1):
-                    pass
+                    if step_ms is not None:
+                        now = time.perf_counter()
+                        step_ms.append((now - t_prev) * 1e3)
+                        t_prev = now
             return last
+
+        def allocations():
+            dev_stats = torch.cuda.memory_stats(dev)
+            host_stats = torch.cuda.host_memory_stats() if hasattr(torch.cuda, "host_memory_stats") else {}
+            return (dev_stats.get("num_device_alloc", 0), host_stats.get("num_host_alloc", 0))
 
         # (a) the loader-style public call: `for out in pipeline.stream(batches)` keeps one batch
         # in flight, so the copy-in of step n+1 overlaps the copy-out of step n; (b) the plain
-        # call `pipeline(batch)`, step by step, reported beside it
-        # warm-up: the loop keeps three pinned 2 GiB result buffers alive (in flight, yielded, held by
-        # the consumer); page-locking one takes ~1 s, so they are all created (and released to
-        # torch's pinned-memory cache) before the timed region
+        # call `pipeline(batch)`, step by step, reported beside it.
+        # Warm-up: the loop keeps three pinned 2 GiB result buffers alive (in flight, yielded, held
+        # by the consumer) and page-locking one takes ~0.6 s; device slices are cached by torch's
+        # allocators too.  Warm up until a round of steps allocates nothing new.
         torch.manual_seed(4321 + rank)
-        run_stream(max(4, args.warmup))
+        for _ in range(6):
+            before = allocations()
+            run_stream(max(4, args.warmup))
+            if allocations() == before:
+                break
         barrier()
+        alloc0 = allocations()
+        step_ms = []
         w0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = run_stream(args.steps)
+        res = run_stream(args.steps, step_ms)
         e1.record()
         barrier()
         e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+        alloc1 = allocations()
         assert res.images["t1"].data.device.type == "cpu"
         for _ in range(2):
             res = step(host)
@@ -285,7 +300,9 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         sync_ms = (time.perf_counter() - w0) * 1e3 / sync_steps
         moved = host.numel() * 4 + (labels_host.numel() * 2 if args.labels else 0)
-        e2e = {"ms": e2e_ms, "bytes_in": moved, "bytes_out": moved, "sync_ms": sync_ms}
+        e2e = {"ms": e2e_ms, "bytes_in": moved, "bytes_out": moved, "sync_ms": sync_ms,
+               "step_ms": [round(v, 1) for v in step_ms],
+               "new_allocations": [alloc1[0] - alloc0[0], alloc1[1] - alloc0[1]]}
         del res
     ops.resample = raw_resample
 
@@ -387,6 +404,8 @@ def run_b200(args, rank, world, local_rank):
             "api": "for out in pipeline.stream(host_batches, depth=1): one batch in flight, every batch copied"
                    " in from pinned host memory and its result copied back inside the timed region",
             "plain_call_ms_per_step": e2e["sync_ms"],
+            "step_ms": e2e["step_ms"],
+            "new_device_host_allocations_in_timed_region": e2e["new_allocations"],
         }
     if numa is not None:
         line["config"]["numa"] = numa
