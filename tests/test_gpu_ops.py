@@ -472,3 +472,43 @@ def test_stream_yields_what_the_plain_calls_return():
     ticket = make().submit(next(batches()))
     out = ticket.result()
     assert ticket.done() and out.images["t1"].data.device.type == "cpu"
+
+
+def test_remap_vector_path_equals_c_oracle():
+    """tio_remap's 128-bit path (rows that are multiples of 16 bytes): aligned / unaligned crops,
+    every padding mode, flips along every axis (a K flip reverses the unit in registers), all
+    element sizes — bit for bit against the C oracle."""
+    from torchio_b200 import ops
+
+    c_port = _orc()
+    rng = np.random.default_rng(12)
+    g = torch.Generator().manual_seed(12)
+    for trial in range(48):
+        dtype = [torch.float32, torch.int16, torch.uint8, torch.int64][trial % 4]
+        shape = (int(rng.integers(5, 9)), int(rng.integers(5, 9)), 16 * int(rng.integers(1, 4)))
+        x = (torch.rand((2, 2, *shape), generator=g) * 90).to(dtype)
+        mode = ["constant", "replicate", "reflect", "circular"][(trial // 4) % 4]
+        # K padding in multiples that keep the output row a multiple of 16 elements or not
+        pad = [int(rng.integers(0, 4)) for _ in range(4)] + [int(rng.integers(0, 5)) * (4 if trial % 3 else 1),
+                                                             int(rng.integers(0, 5)) * (4 if trial % 3 else 1)]
+        pad[5] += (-(shape[2] + pad[4] + pad[5])) % 16  # output K a multiple of 16: vector path for every dtype
+        if mode in ("reflect", "circular"):
+            pad = [min(p, s - 1) for p, s in zip(pad, (shape[0], shape[0], shape[1], shape[1], shape[2], shape[2]))]
+            pad[5] -= (shape[2] + pad[4] + pad[5]) % 16 if (shape[2] + pad[4] + pad[5]) % 16 <= pad[5] else 0
+        out_shape = tuple(shape[a] + pad[2 * a] + pad[2 * a + 1] for a in range(3))
+        offsets = (pad[0], pad[2], pad[4])
+        bits = [int(rng.integers(0, 8)) for _ in range(2)]
+        want = c_port.remap(x, out_shape, offsets, mode=mode, fill=7, flip_bits=bits)
+        got = ops.remap(x.cuda(), out_shape, offsets, mode=mode, fill=7,
+                        flip=torch.tensor(bits, dtype=torch.uint8, device="cuda")).cpu()
+        assert torch.equal(got, want), (trial, dtype, mode, pad, bits)
+        # crop back (negative offsets), aligned and unaligned starts along K
+        back_shape = (shape[0], shape[1], 16)
+        for k_off in (0, 3, 4):
+            if pad[4] + k_off + 16 > out_shape[2]:
+                continue
+            offs = (-pad[0], -pad[2], -(pad[4] + k_off))
+            want_b = c_port.remap(want, back_shape, offs, flip_bits=bits)
+            got_b = ops.remap(want.cuda(), back_shape, offs,
+                              flip=torch.tensor(bits, dtype=torch.uint8, device="cuda")).cpu()
+            assert torch.equal(got_b, want_b), (trial, dtype, k_off, bits)

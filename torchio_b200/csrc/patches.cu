@@ -6,6 +6,8 @@
 // data/batch.py:52-58).  On the device one launch gathers all `n` patches of a
 // volume into a dense (n, C, pi, pj, pk) block, reading every source byte once.
 // Pure data movement: bound by HBM, algorithmic bytes = 2 x patch bytes.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tio {
@@ -156,6 +158,59 @@ remap_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int I
   }
 }
 
+// 16 bytes of an output row per thread (rows that are multiples of 16 bytes, 16-byte aligned
+// destination): one 128-bit store; the source elements come with one 128-bit load when the unit
+// maps to an in-range, unflipped, aligned run of the source row, element by element otherwise
+// (padding, flips along K, unaligned crops).
+template <typename T>
+__global__ void __launch_bounds__(256)
+remap_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int I, int J, int K, int OI,
+                 int OJ, int OK, int off_i, int off_j, int off_k, int mode, T fill,
+                 const uint8_t* __restrict__ flip, long long units) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*C*OI*OJ*(OK/V)
+  if (u >= units) return;
+  const int per_row = OK / V;
+  const long long row = u / per_row;
+  const int ok0 = (int)(u - row * per_row) * V;
+  const int oj = (int)(row % OJ);
+  const int oi = (int)((row / OJ) % OI);
+  const long long bc = row / ((long long)OJ * OI);
+  const int b = (int)(bc / C);
+  const uint8_t fl = flip ? __ldg(flip + b) : 0;
+  bool outside = false;
+  int si = remap_index(oi - off_i, I, mode, outside);
+  int sj = remap_index(oj - off_j, J, mode, outside);
+  if (fl & 1) si = I - 1 - si;
+  if (fl & 2) sj = J - 1 - sj;
+  const T* s = src + ((bc * I + si) * J + sj) * K;
+  const int sk0 = ok0 - off_k;
+  uint4 v;
+  const bool whole = !outside && sk0 >= 0 && sk0 + V <= K;  // the unit maps to V in-range source elements
+  const int first = (fl & 4) ? K - V - sk0 : sk0;           // ... which start here (mirrored run when flipped)
+  if (whole && ((uintptr_t)(s + first) & 15) == 0) {
+    v = __ldg(reinterpret_cast<const uint4*>(s + first));
+    if (fl & 4) {  // reverse the V elements in registers
+      T t[V], r[V];
+      memcpy(t, &v, 16);
+#pragma unroll
+      for (int e = 0; e < V; ++e) r[e] = t[V - 1 - e];
+      memcpy(&v, r, 16);
+    }
+  } else {
+    T t[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      bool out_k = outside;
+      int sk = remap_index(sk0 + e, K, mode, out_k);
+      if (fl & 4) sk = K - 1 - sk;
+      t[e] = out_k ? fill : __ldg(s + sk);
+    }
+    memcpy(&v, t, 16);
+  }
+  *reinterpret_cast<uint4*>(dst + row * OK + ok0) = v;
+}
+
 template <typename T>
 static void launch_remap(const void* src, void* dst, int B, int C, int I, int J, int K, int OI, int OJ,
                          int OK, int oi, int oj, int ok, int mode, unsigned long long fill_bits,
@@ -163,6 +218,17 @@ static void launch_remap(const void* src, void* dst, int B, int C, int I, int J,
   T fill;
   memcpy(&fill, &fill_bits, sizeof(T));
   const long long rows = (long long)B * C * OI * OJ;
+  constexpr int V = 16 / (int)sizeof(T);
+  static const bool scalar_only = []() {  // TIO_B200_REMAP_SCALAR=1: development knob (A/B timing)
+    const char* e = getenv("TIO_B200_REMAP_SCALAR");
+    return e && e[0] == '1';
+  }();
+  if (!scalar_only && OK % V == 0 && ((uintptr_t)dst & 15) == 0 && rows * (OK / V) / 256 < (1ll << 31)) {
+    const long long units = rows * (OK / V);
+    remap_vec_kernel<T><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(
+        (const T*)src, (T*)dst, B, C, I, J, K, OI, OJ, OK, oi, oj, ok, mode, fill, flip, units);
+    return;
+  }
   const int tx = OK >= 128 ? 128 : (OK >= 64 ? 64 : 32);
   dim3 block(tx, 256 / tx);
   const unsigned blocks = (unsigned)((rows + block.y - 1) / block.y);
