@@ -80,7 +80,8 @@ int tio_abi_version(void);
  *              the trilinear weight of every label among the 8 taps is accumulated in
  *              grid_sample's corner order, the largest wins (smallest label on ties, as
  *              argmax over torch.unique's ascending channels), and voxels whose in-bounds
- *              weight is not > 0.5 take the pad label.  Any dtype; general gather kernel.
+ *              weight is not > 0.5 take the pad label.  u8 / i16 / i32 take the TMA tile path
+ *              (box_hint >= 0 and a workspace), any other dtype the general gather kernel.
  *   fill       [C] fp32 per-channel fill, or NULL = skip the mask step
  *              (the reference skips it only for a python-float 0.0 fill,
  *              spatial.py:2072-2076).  The mask is always the TRILINEAR

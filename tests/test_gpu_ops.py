@@ -512,3 +512,50 @@ def test_remap_vector_path_equals_c_oracle():
             got_b = ops.remap(want.cuda(), back_shape, offs,
                               flip=torch.tensor(bits, dtype=torch.uint8, device="cuda")).cpu()
             assert torch.equal(got_b, want_b), (trial, dtype, k_off, bits)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int16, torch.int32])
+@pytest.mark.parametrize("elastic", [False, True])
+def test_label_pv_tile_path_is_bit_exact_with_general_path_and_oracle(dtype, elastic):
+    """label_interpolation="label" (TIO_LABEL_PV) through the TMA tile kernel == the general gather
+    kernel == the oracle's one-hot / grid_sample / argmax restatement, on blocky label maps
+    (boundaries everywhere), with big translations so that border tiles skip out-of-volume corners,
+    and with an exactly axis-aligned half-voxel shift (argmax ties on every boundary voxel)."""
+    from oracle import torch_port
+    from torchio_b200 import ops
+
+    rng = np.random.default_rng(77)
+    shape = (48, 48, 64)
+    i, j, k = (torch.arange(n) for n in shape)
+    lab = (((i[:, None, None] // 5) * 3 + (j[None, :, None] // 7) * 5 + (k[None, None, :] // 6)) % 6)
+    lab = torch.stack([lab, (lab * 7 + 1) % 5, lab.flip(0)]).to(dtype)[:, None].contiguous()  # (3,1,...)
+    mats = []
+    for b in range(3):
+        ang = rng.uniform(-0.2, 0.2, 3)
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        r = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+             @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])) * rng.uniform(0.9, 1.1)
+        c = (np.array(shape) - 1) / 2
+        m = np.eye(4); m[:3, :3] = r; m[:3, 3] = c - r @ c + rng.uniform(-6, 6, 3)
+        mats.append(m)
+    mats[2] = np.eye(4); mats[2][:3, 3] = (0.5, -0.5, 1.5)  # exact ties
+    mat = torch.tensor(np.stack([m.astype(np.float32)[:3].reshape(12) for m in mats])).cuda()
+    cp = flags = None
+    if elastic:
+        cp = torch.tensor(rng.uniform(-4, 4, (3, 7, 7, 7, 3)).astype(np.float32)).cuda()
+        flags = torch.tensor([2, 2, 0], dtype=torch.uint8).cuda()
+    one = (1.0, 1.0, 1.0)
+    pad = torch.tensor([9.0]).cuda()
+    kw = dict(affine_first=True, mode=ops.LABEL_PV, fill=pad)
+    tiled = ops.resample(lab.cuda(), mat, cp, flags, one, one, **kw)
+    general = ops.resample(lab.cuda(), mat, cp, flags, one, one, box_hint=-1, **kw)
+    assert tiled.dtype == dtype
+    assert torch.equal(tiled, general), int((tiled != general).sum())
+    # the oracle's restatement element by element (its sampling grid from the same tables)
+    for b in range(3):
+        if elastic and b < 2:
+            continue  # the displacement part of the grid is covered by the golden fixtures
+        a_in = np.eye(4)
+        grid = torch_port.map_homogeneous(torch_port.voxel_coordinates(shape), torch.tensor(mats[b], dtype=torch.float64).float())
+        want = torch_port.label_partial_volume(lab[b:b + 1], grid, shape, a_in, a_in, False, "linear", 9.0)
+        assert torch.equal(general[b:b + 1].cpu(), want), (b, int((general[b:b + 1].cpu() != want).sum()))

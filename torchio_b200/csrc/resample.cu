@@ -195,7 +195,7 @@ extern "C" int tio_resample(const void* src, void* dst, int dtype, int B, int C,
   a.affine_first = affine_first;
   a.cp_in_smem = cp && ((size_t)ni * nj * nk * 12 <= 96 * 1024);
   cudaStream_t st = (cudaStream_t)stream;
-  if (box_hint >= 0 && mode != TIO_LABEL_PV) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
+  if (box_hint >= 0) {  // fp32 trilinear and 1/2/4-byte nearest take the TMA tile path when it applies
     const int rc = launch_resample_tile(a, dtype, mode, exact_coords, box_hint, workspace, workspace_bytes, st);
     if (rc == 0) {
       TIO_CHECK_LAUNCH();

@@ -64,6 +64,48 @@ __device__ __forceinline__ float renormalise(float q, float nm1, float sm1) {
 }
 
 
+// label_interpolation="label" for one voxel (spatial.py:1275-1389, C == 1): the sampled value of a
+// one-hot channel is the sum, in grid_sample's corner order, of the weights of the corners that
+// carry its label (1 * w and + 0 * w are exact), so only the labels of the 8 taps matter.  Labels
+// are visited in ascending order (torch.unique's channel order): the largest sum wins, the first
+// on ties (argmax), and the sequential channel sum decides in-bounds (> 0.5) vs pad label.
+// `active`: bit t set = corner t is inside the volume (out-of-bounds corners are skipped).
+template <typename T>
+__device__ __forceinline__ T label_pv_pick(const T tap[8], const float w[8], const unsigned active, const T pad) {
+  if (active == 0u) return pad;
+  // one label on every corner (the inside of a region, i.e. most voxels): its channel is the
+  // ordered sum of the active weights, every other channel is exactly 0
+  {
+    T first = tap[7];
+#pragma unroll
+    for (int t = 6; t >= 0; --t)  // the lowest active corner (no dynamic register indexing)
+      if ((active >> t) & 1u) first = tap[t];
+    bool same = true;
+    float s = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if ((active >> t) & 1u) { same = same && (tap[t] == first); s = __fadd_rn(s, w[t]); }
+    if (same) return (s > 0.5f) ? first : pad;
+  }
+  unsigned todo = active;
+  float total = 0.0f, best_s = -1.0f;
+  T best = (T)0;
+  while (todo) {
+    T lab = (T)0;
+    bool have = false;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (((todo >> t) & 1u) && (!have || tap[t] < lab)) { lab = tap[t]; have = true; }
+    float s = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (((active >> t) & 1u) && tap[t] == lab) { s = __fadd_rn(s, w[t]); todo &= ~(1u << t); }
+    total = __fadd_rn(total, s);  // sampled.sum(dim=1): ascending label order
+    if (s > best_s) { best_s = s; best = lab; }
+  }
+  return (total > 0.5f) ? best : pad;
+}
+
 // General per-thread column: walks output planes [oi0, oi_end) at (oj, ok),
 // gathering straight from global memory with exact ATen rounding everywhere
 // (bit-exact with oracle/c/tio_oracle.c for every dtype and mode).
@@ -194,13 +236,7 @@ __device__ __forceinline__ void general_column(const ResampleArgs& a, const int 
         dst[c * n_out + o_off] = v;
       }
     } else if (MODE == TIO_LABEL_PV) {
-      // Partial-volume label resampling (spatial.py:1275-1389, C == 1): one-hot per label value,
-      // trilinear sample of every channel (zero padding, no mask step: the sampler is called with
-      // a python-float 0.0 fill), argmax over the channels in ascending label order (first
-      // maximum wins), default_pad_label where the channel sum is not > 0.5.  A one-hot channel
-      // sampled by grid_sample is the sum, in corner order, of the weights of the corners that
-      // carry its label (1 * w and + 0 * w are exact), so only the labels of the 8 taps matter:
-      // every other channel is exactly 0 and can neither win nor move the sum.
+      // partial-volume label resampling: see label_pv_pick
       const int64_t base = ((int64_t)c0 * a.J + c1) * a.K + c2;
       const int64_t sI = (int64_t)a.J * a.K, sJ = a.K;
       T tap[8];
@@ -211,23 +247,7 @@ __device__ __forceinline__ void general_column(const ResampleArgs& a, const int 
         tap[t] = act ? __ldg(src + base + (t & 1) * sI + ((t >> 1) & 1) * sJ + ((t >> 2) & 1)) : (T)0;
         todo |= act ? (1u << t) : 0u;
       }
-      const unsigned active = todo;
-      float total = 0.0f, best_s = -1.0f;
-      T best = (T)0;
-      while (todo) {
-        T lab = (T)0;
-        bool have = false;
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (((todo >> t) & 1u) && (!have || tap[t] < lab)) { lab = tap[t]; have = true; }
-        float s = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (((active >> t) & 1u) && tap[t] == lab) { s = __fadd_rn(s, w[t]); todo &= ~(1u << t); }
-        total = __fadd_rn(total, s);  // sampled.sum(dim=1): ascending label order
-        if (s > best_s) { best_s = s; best = lab; }
-      }
-      dst[o_off] = (total > 0.5f) ? best : ElemTraits<T>::from_f32(a.fill[0]);
+      dst[o_off] = label_pv_pick<T>(tap, w, todo, ElemTraits<T>::from_f32(a.fill[0]));
     } else {
       const int64_t base = ((int64_t)c0 * a.J + c1) * a.K + c2;
       const int64_t sI = (int64_t)a.J * a.K, sJ = a.K;

@@ -107,6 +107,40 @@ __device__ __forceinline__ void walk_column(
            ((unsigned)c2 < (unsigned)(a.K - 1));
   };
 
+  // partial-volume label value at exact coordinates (u0, u1, u2): the weights in the reference's
+  // order, the 8 label taps from the box, corners outside the volume skipped (CHECK tiles)
+  auto label_pv = [&](const float u0, const float u1, const float u2) -> T {
+    const float s0 = __fadd_rd(u0, kMagic), s1 = __fadd_rd(u1, kMagic), s2 = __fadd_rd(u2, kMagic);
+    const float f0 = __fsub_rn(s0, kMagic), f1 = __fsub_rn(s1, kMagic), f2_ = __fsub_rn(s2, kMagic);
+    const float hi0 = __fsub_rn(u0, f0), hi1 = __fsub_rn(u1, f1), hi2 = __fsub_rn(u2, f2_);
+    const float lo0 = __fsub_rn(__fadd_rn(f0, 1.0f), u0), lo1 = __fsub_rn(__fadd_rn(f1, 1.0f), u1),
+                lo2 = __fsub_rn(__fadd_rn(f2_, 1.0f), u2);
+    const float w00 = __fmul_rn(lo0, lo1), w10 = __fmul_rn(hi0, lo1);
+    const float w01 = __fmul_rn(lo0, hi1), w11 = __fmul_rn(hi0, hi1);
+    float w[8];
+    w[0] = __fmul_rn(w00, lo2); w[1] = __fmul_rn(w10, lo2); w[2] = __fmul_rn(w01, lo2); w[3] = __fmul_rn(w11, lo2);
+    w[4] = __fmul_rn(w00, hi2); w[5] = __fmul_rn(w10, hi2); w[6] = __fmul_rn(w01, hi2); w[7] = __fmul_rn(w11, hi2);
+    const int b0 = __float_as_int(s0), b1 = __float_as_int(s1), b2 = __float_as_int(s2);
+    const uint32_t addr = kbase + (((unsigned)b0 * C1 + (unsigned)b1 * C2 + (unsigned)b2) << ESH);
+    unsigned active = 0xffu;
+    if (CHECK) {
+      const int c0 = b0 - kMagicBits, c1 = b1 - kMagicBits, c2 = b2 - kMagicBits;
+      if (!interior(c0, c1, c2)) {
+        const bool il = (unsigned)c0 < (unsigned)a.I, ih = (unsigned)(c0 + 1) < (unsigned)a.I;
+        const bool jl = (unsigned)c1 < (unsigned)a.J, jh = (unsigned)(c1 + 1) < (unsigned)a.J;
+        const bool kl = (unsigned)c2 < (unsigned)a.K, kh = (unsigned)(c2 + 1) < (unsigned)a.K;
+        active = (il & jl & kl ? 1u : 0u) | (ih & jl & kl ? 2u : 0u) | (il & jh & kl ? 4u : 0u) |
+                 (ih & jh & kl ? 8u : 0u) | (il & jl & kh ? 16u : 0u) | (ih & jl & kh ? 32u : 0u) |
+                 (il & jh & kh ? 64u : 0u) | (ih & jh & kh ? 128u : 0u);
+      }
+    }
+    T tap[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)  // corner t: +1 in I (bit 0), J (bit 1), K (bit 2)
+      tap[t] = lds_elem<T>(addr + ((unsigned)((t & 1) * C1 + ((t >> 1) & 1) * C2 + ((t >> 2) & 1)) << ESH));
+    return label_pv_pick<T>(tap, w, active, ElemTraits<T>::from_f32(fill_c));
+  };
+
   // ---- one plane (odd tail, cell changes inside a pair, non-unit spacing) ----
   // (`rel` = plane index within the walk, `pi` = its output coordinate as a float: the loop
   // carries both so that nothing has to be re-derived from blockIdx inside it)
@@ -149,6 +183,10 @@ __device__ __forceinline__ void walk_column(
       const int r0 = __float_as_int(__fadd_rn(u0, kMagic)), r1 = __float_as_int(__fadd_rn(u1, kMagic)),
                 r2 = __float_as_int(__fadd_rn(u2, kMagic));
       *dst = lds_elem<T>(kbase + (((unsigned)r0 * C1 + (unsigned)r1 * C2 + (unsigned)r2) << ESH));
+      return;
+    }
+    if (MODE == TIO_LABEL_PV) {
+      *dst = label_pv(u0, u1, u2);
       return;
     }
     // floor via round-down magic add: the mantissa holds floor(u)
@@ -248,6 +286,13 @@ __device__ __forceinline__ void walk_column(
                           (unsigned)__float_as_int(r2b);
       out[0] = lds_elem<T>(kbase + (na << ESH));
       out[ostride] = lds_elem<T>(kbase + (nb << ESH));
+      continue;
+    }
+    if (MODE == TIO_LABEL_PV) {
+      float u0a, u0b, u1a, u1b, u2a, u2b;
+      unpack2(u0, u0a, u0b); unpack2(u1, u1a, u1b); unpack2(u2, u2a, u2b);
+      out[0] = label_pv(u0a, u1a, u2a);
+      out[ostride] = label_pv(u0b, u1b, u2b);
       continue;
     }
     const f2 s0 = add2_rd(u0, magic2), s1 = add2_rd(u1, magic2), s2 = add2_rd(u2, magic2);
@@ -456,9 +501,10 @@ resample_tile_kernel(const __grid_constant__ CUtensorMap tmap, const ResampleArg
       const bool chk = HAS_FILL && !tile_interior;
 #define TIO_WALK(CHK, EM)                                                                            \
   walk_column<BOX, T, MODE, HAS_CP, CHK, FASTDIV, EM>(a, ta, box, cps, li_tab, li_pairs, m, elastic, identity, \
-                                             kbase, i0, i1, oj, ok, chk ? a.fill[c] : 0.0f, out, ostride)
+                                             kbase, i0, i1, oj, ok,                                         \
+                                             (chk || MODE == TIO_LABEL_PV) ? a.fill[c] : 0.0f, out, ostride)
       bool walked = false;
-      if constexpr (MODE == TIO_LINEAR && HAS_FILL) {
+      if constexpr ((MODE == TIO_LINEAR || MODE == TIO_LABEL_PV) && HAS_FILL) {
         if (chk) {
           walked = true;
           if (emode == 0) TIO_WALK(true, 0);
@@ -574,6 +620,20 @@ static void launch_nearest(int box, const CUtensorMap& tm, const ResampleArgs& a
   }
 }
 
+// partial-volume label maps (TIO_LABEL_PV): same boxes and admitted-division variants as nearest;
+// the pad label is always present (HAS_FILL)
+template <typename T>
+static void launch_label_pv(int box, const CUtensorMap& tm, const ResampleArgs& a, const TileArgs& ta,
+                            dim3 grid, size_t smem, const int4* records, cudaStream_t st) {
+  if (box == 24) {
+    if (a.cp) launch_tile<24, T, TIO_LABEL_PV, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<24, T, TIO_LABEL_PV, false, true>(tm, a, ta, grid, smem, records, st);
+  } else {
+    if (a.cp) launch_tile<32, T, TIO_LABEL_PV, true, true>(tm, a, ta, grid, smem, records, st);
+    else launch_tile<32, T, TIO_LABEL_PV, false, true>(tm, a, ta, grid, smem, records, st);
+  }
+}
+
 // Returns 0 when launched, 1 when the fast path does not apply (caller falls back),
 // >1 on error.
 size_t resample_tile_workspace_bytes(int B, int OI, int OJ, int OK) {
@@ -596,7 +656,7 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
   // supported box edges; 0 (auto) = 24
   int box = 24;
   if (box_hint > 0) box = box_hint <= 20 ? 20 : box_hint <= 22 ? 22 : box_hint <= 24 ? 24 : box_hint <= 28 ? 28 : 32;
-  if (mode == TIO_NEAREST) box = box <= 24 ? 24 : 32;
+  if (mode != TIO_LINEAR) box = box <= 24 ? 24 : 32;
   const int tiles_i = (a.OI + XT - 1) / XT;
   if ((int64_t)a.B * tiles_i > 65535 || (a.OJ + XT - 1) / XT > 65535) return 1;
 
@@ -652,7 +712,7 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
   if (!workspace || workspace_bytes < (size_t)n_tiles * sizeof(int4) || ((uintptr_t)workspace & 15)) return 1;
   int4* records = (int4*)workspace;
   const unsigned bounds_blocks = (unsigned)((n_tiles + 127) / 128);
-  if (mode == TIO_NEAREST && !fast) return 1;
+  if (mode != TIO_LINEAR && !fast) return 1;
   // elastic launches of the fast kernel: most tiles need far less than the launch's box (the
   // displacement is smooth, its borders are locked) and load a small box instead
   const bool dual = !exact_coords && mode == TIO_LINEAR && a.cp && box > kSmallBox;
@@ -668,6 +728,12 @@ int launch_resample_tile(const ResampleArgs& a, int dtype, int mode, bool exact_
   if (a.cp) tile_bounds_kernel<true><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, box_s, bk_s, records);
   else tile_bounds_kernel<false><<<bounds_blocks, 128, 0, st>>>(a, box, kalign, bk, box_s, bk_s, records);
   const size_t smem = ((size_t)box * box * bk * esize + 15) / 16 * 16 + kAuxFloats * sizeof(float);
+  if (mode == TIO_LABEL_PV) {
+    if (dtype == TIO_U8) launch_label_pv<uint8_t>(box, tm, a, ta, grid, smem, records, st);
+    else if (dtype == TIO_I16) launch_label_pv<int16_t>(box, tm, a, ta, grid, smem, records, st);
+    else launch_label_pv<int32_t>(box, tm, a, ta, grid, smem, records, st);
+    return 0;
+  }
   if (mode == TIO_NEAREST) {
     if (dtype == TIO_U8) launch_nearest<uint8_t>(box, tm, a, ta, grid, smem, records, st);
     else if (dtype == TIO_I16) launch_nearest<int16_t>(box, tm, a, ta, grid, smem, records, st);

@@ -202,7 +202,7 @@ def resample(
     sp_out = np.asarray(spacing_out, dtype=np.float32)
     workspace, ws_bytes = None, 0
     tiled = (src.dtype == torch.float32 and mode == LINEAR) or (
-        mode == NEAREST and src.dtype in (torch.uint8, torch.int16, torch.int32))
+        mode in (NEAREST, LABEL_PV) and src.dtype in (torch.uint8, torch.int16, torch.int32))
     if box_hint >= 0 and tiled:
         ws_bytes = _native.lib().tio_resample_workspace_bytes(b, oi, oj, ok)
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=src.device)
