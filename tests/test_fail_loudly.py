@@ -29,7 +29,12 @@ def _batch(b=2):
     lambda tio: tio.Gamma(log_gamma=(-0.2, 0.2)), lambda tio: tio.Flip(axes=0), lambda tio: tio.Pad(padding=1),
     lambda tio: tio.Crop(cropping=1), lambda tio: tio.CropOrPad(6),
     lambda tio: tio.Compose([tio.Affine(degrees=(-5, 5)), tio.Gamma(log_gamma=(-0.2, 0.2))]),
-], ids=["Affine", "Elastic", "BiasField", "Blur", "Noise", "Gamma", "Flip", "Pad", "Crop", "CropOrPad", "Compose"])
+    lambda tio: tio.Standardize(), lambda tio: tio.Normalize(),
+    lambda tio: tio.Pad(padding=1, padding_mode="median"), lambda tio: tio.Pad(padding=1, padding_mode="minimum"),
+    lambda tio: tio.Affine(degrees=(-5, 5), default_pad_value="otsu"),
+    lambda tio: tio.Resample(2, antialias=True),
+], ids=["Affine", "Elastic", "BiasField", "Blur", "Noise", "Gamma", "Flip", "Pad", "Crop", "CropOrPad", "Compose",
+        "Standardize", "Normalize", "PadMedian", "PadMinimum", "AffineOtsu", "ResampleAntialias"])
 def test_transforms_raise_without_cuda(make):
     import torchio_b200 as tio
 
@@ -41,6 +46,41 @@ def test_transforms_raise_without_cuda(make):
 
 
 @cpu_only
+def test_label_partial_volume_raises_without_cuda():
+    import torchio_b200 as tio
+
+    lab = (torch.rand((2, 1, 8, 8, 8)) * 4).to(torch.int16)
+    batch = tio.SubjectsBatch({"seg": tio.ImagesBatch(lab, [tio.AffineMatrix() for _ in range(2)],
+                                                      image_class=tio.LabelMap)})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for kwargs in ({}, {"antialias": True}):
+            with pytest.raises(RuntimeError, match="CUDA"):
+                tio.Spatial(degrees=(-5, 5), label_interpolation="label", copy=False, **kwargs)(batch)
+
+
+def test_stream_validates_depth_before_touching_a_batch():
+    import torchio_b200 as tio
+
+    pipe = tio.Compose([], copy=False)
+    with pytest.raises(ValueError, match="depth"):
+        list(pipe.stream(iter([_batch()]), depth=-1))
+
+
+@cpu_only
+def test_stream_and_submit_raise_without_cuda():
+    import torchio_b200 as tio
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pipe = tio.Compose([tio.Gamma(log_gamma=(-0.2, 0.2))], copy=False)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pipe.submit(_batch())
+        with pytest.raises(RuntimeError, match="CUDA"):
+            list(pipe.stream(iter([_batch(), _batch()]), depth=1))
+
+
+@cpu_only
 def test_ops_raise_on_host_tensors():
     from torchio_b200 import ops
 
@@ -49,6 +89,15 @@ def test_ops_raise_on_host_tensors():
         ops.gamma(x, torch.ones(1))
     with pytest.raises((RuntimeError, ValueError, TypeError)):
         ops.crop_patches(x[0], [[0, 0, 0]], (4, 4, 4))
+    lab = (x * 4).to(torch.int16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.onehot(lab, torch.arange(4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.label_argmax(torch.rand((1, 4, 8, 8, 8)), torch.arange(4), 0.0, torch.int16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.remap(x, (8, 8, 8), (0, 0, 0))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.rescale(x, sub=0.5)
 
 
 def test_package_never_imports_the_oracle():
