@@ -120,6 +120,27 @@ def bind_to_gpu_numa(local_rank: int) -> dict | None:
         if not allowed:
             return None
         os.sched_setaffinity(0, allowed)
-        return {"node": node, "cpus": len(allowed), "gpu_bus": bus}
+        return {"node": node, "cpus": len(allowed), "gpu_bus": bus, "mempolicy": _prefer_memory_node(node)}
     except (OSError, ValueError, subprocess.SubprocessError):
+        return None
+
+
+def _prefer_memory_node(node: int) -> str | None:
+    """`set_mempolicy(MPOL_PREFERRED, node)` for the calling thread (inherited by the threads it
+    starts): pages allocated from now on — the page-locked staging buffers in particular — come
+    from the GPU's NUMA node even when the allocating thread is not the one bound above.  Soft
+    preference (falls back to other nodes when the node is full).  Returns "preferred" or None when
+    the call is unavailable (then placement is first-touch, as before)."""
+    import ctypes
+    import platform
+
+    number = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+    if number is None or not 0 <= node < 64:
+        return None
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        mpol_preferred = 1
+        return "preferred" if libc.syscall(number, mpol_preferred, ctypes.byref(mask), 65) == 0 else None
+    except (OSError, AttributeError):
         return None
