@@ -62,7 +62,11 @@ class Compose(Transform):
         for the last copy-out and hands back what `forward` returns.  Anything else is
         executed as `forward` does and the ticket is already complete.  Submitting batch
         n+1 before collecting batch n lets its copy-in overlap the copy-out of batch n
-        (PCIe is full duplex) — `stream` does exactly that."""
+        (PCIe is full duplex) — `stream` does exactly that.
+
+        Until `result()` returns, the device is still reading the host tensors of ``data``: a
+        loader that refills one staging buffer in place must not touch it before then (fresh
+        tensors per batch, as `SubjectsLoader` / `DataLoader` produce, are fine)."""
         if self.copy:
             data = _copy.deepcopy(data)
         batch, unwrap = wrap_input(data)
@@ -78,7 +82,8 @@ class Compose(Transform):
         """Loader-style application: ``for out in pipeline.stream(loader)`` yields
         ``pipeline(batch)`` for every batch of ``loader``, in order, with up to ``depth``
         later batches already issued to the device while the caller consumes the current one.
-        Results and RNG consumption equal calling the pipeline batch by batch."""
+        Results and RNG consumption equal calling the pipeline batch by batch.  ``batches`` must
+        yield tensors it does not overwrite while they are in flight (see `submit`)."""
         if depth < 0:
             raise ValueError(f"depth must be >= 0, got {depth}")
         window: list[Pending] = []
