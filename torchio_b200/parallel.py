@@ -138,9 +138,11 @@ def _prefer_memory_node(node: int) -> str | None:
     if number is None or not 0 <= node < 64:
         return None
     try:
-        libc = ctypes.CDLL(None, use_errno=True)
+        syscall = ctypes.CDLL(None, use_errno=True).syscall
+        syscall.restype = ctypes.c_long
+        syscall.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_void_p, ctypes.c_ulong]
         mask = ctypes.c_ulong(1 << node)
         mpol_preferred = 1
-        return "preferred" if libc.syscall(number, mpol_preferred, ctypes.byref(mask), 65) == 0 else None
+        return "preferred" if syscall(number, mpol_preferred, ctypes.addressof(mask), 65) == 0 else None
     except (OSError, AttributeError):
         return None
